@@ -10,8 +10,11 @@ measured on synthetic data of the reference's shapes:
   drawn from the same distributions ``nn.Linear``'s default init uses, then re-scaled so that
   matching is non-degenerate (plain random init yields 0 matches and never stops/prunes).
 
-Everything here is generated from an explicit ``torch.Generator`` on the CPU, so the same seed
-gives bit-identical tensors here, in the golden-fixture generator and on the GPU box.
+Everything here is generated from an explicit ``torch.Generator`` on the CPU using only operations
+that are bit-reproducible across CPUs (uniform draws, exact fp64 sums, correctly-rounded
+elementwise IEEE ops): no ``randn`` (its vectorised Box-Muller differs in the last ulp between
+AVX2/AVX-512 hosts) and no fp32 reductions (``normalize``).  The same seed therefore gives
+bit-identical tensors in the build container, in the golden-fixture generator and on the GPU box.
 """
 from __future__ import annotations
 
@@ -22,6 +25,23 @@ import torch
 
 N_LAYERS = 9
 DIM = 256
+
+
+def _gauss(g: torch.Generator, *shape: int) -> torch.Tensor:
+    """~N(0,1) as an Irwin-Hall sum of 12 uniforms, fp64.  Each uniform is a 24-bit fp32 value, so the
+    fp64 sum is exact (order independent); the result is snapped to a 2^-12 grid."""
+    acc = torch.zeros(*shape, dtype=torch.float64)
+    for _ in range(12):
+        acc += torch.rand(*shape, generator=g).double()
+    return torch.round((acc - 6.0) * 4096.0) / 4096.0
+
+
+def _unit_rows(v: torch.Tensor) -> torch.Tensor:
+    """Row-normalise fp64 values that lie on a 2^-20 grid: the sum of squares is exact in fp64
+    (<= 48 significant bits), sqrt and the division are correctly rounded -> reproducible fp32 rows."""
+    v = torch.round(v * 1048576.0) / 1048576.0
+    nrm = (v * v).sum(-1, keepdim=True).sqrt()
+    return (v / nrm).float()
 
 
 def make_pair(
@@ -45,12 +65,12 @@ def make_pair(
     big = max(m, n)
     g = torch.Generator().manual_seed(int(seed))
     k_all = torch.rand(b, big, 2, generator=g) * torch.tensor([w, h])
-    d_all = torch.nn.functional.normalize(torch.randn(b, big, d, generator=g), dim=-1)
+    d_all = _unit_rows(_gauss(g, b, big, d))
     perm = torch.stack([torch.randperm(big, generator=g) for _ in range(b)])
     k1 = torch.gather(k_all, 1, perm[..., None].expand(-1, -1, 2))
-    k1 = k1 + 2.0 * torch.randn(b, big, 2, generator=g)
+    k1 = (k1.double() + 2.0 * _gauss(g, b, big, 2)).float()
     d1 = torch.gather(d_all, 1, perm[..., None].expand(-1, -1, d))
-    d1 = torch.nn.functional.normalize(d1 + noise * torch.randn(b, big, d, generator=g), dim=-1)
+    d1 = _unit_rows(d1.double() + noise * _gauss(g, b, big, d))
     size = torch.tensor([[w, h]]).expand(b, 2).contiguous()
     f0 = {"keypoints": k_all[:, :m].contiguous(), "descriptors": d_all[:, :m].contiguous(), "image_size": size}
     f1 = {"keypoints": k1[:, :n].contiguous(), "descriptors": d1[:, :n].contiguous(), "image_size": size.clone()}
@@ -89,22 +109,22 @@ def make_state_dict(
     if input_dim != d:
         sd["input_proj.weight"], sd["input_proj.bias"] = _linear(g, d, input_dim)
     pos_dim = 4 if add_scale_ori else 2
-    sd["posenc.Wr.weight"] = torch.randn(32, pos_dim, generator=g)  # normal(0, gamma**-2), gamma = 1
+    sd["posenc.Wr.weight"] = _gauss(g, 32, pos_dim).float()  # normal(0, gamma**-2), gamma = 1
     for i in range(n_layers):
         p = f"transformers.{i}.self_attn."
         sd[p + "Wqkv.weight"], sd[p + "Wqkv.bias"] = _linear(g, 3 * d, d)
         sd[p + "out_proj.weight"], sd[p + "out_proj.bias"] = _linear(g, d, d)
         sd[p + "ffn.0.weight"], sd[p + "ffn.0.bias"] = _linear(g, 2 * d, 2 * d)
-        sd[p + "ffn.1.weight"] = 1.0 + 0.1 * torch.randn(2 * d, generator=g)
-        sd[p + "ffn.1.bias"] = 0.05 * torch.randn(2 * d, generator=g)
+        sd[p + "ffn.1.weight"] = (1.0 + 0.1 * _gauss(g, 2 * d)).float()
+        sd[p + "ffn.1.bias"] = (0.05 * _gauss(g, 2 * d)).float()
         sd[p + "ffn.3.weight"], sd[p + "ffn.3.bias"] = _linear(g, d, 2 * d)
         p = f"transformers.{i}.cross_attn."
         sd[p + "to_qk.weight"], sd[p + "to_qk.bias"] = _linear(g, d, d)
         sd[p + "to_v.weight"], sd[p + "to_v.bias"] = _linear(g, d, d)
         sd[p + "to_out.weight"], sd[p + "to_out.bias"] = _linear(g, d, d)
         sd[p + "ffn.0.weight"], sd[p + "ffn.0.bias"] = _linear(g, 2 * d, 2 * d)
-        sd[p + "ffn.1.weight"] = 1.0 + 0.1 * torch.randn(2 * d, generator=g)
-        sd[p + "ffn.1.bias"] = 0.05 * torch.randn(2 * d, generator=g)
+        sd[p + "ffn.1.weight"] = (1.0 + 0.1 * _gauss(g, 2 * d)).float()
+        sd[p + "ffn.1.bias"] = (0.05 * _gauss(g, 2 * d)).float()
         sd[p + "ffn.3.weight"], sd[p + "ffn.3.bias"] = _linear(g, d, 2 * d)
     for i in range(n_layers):
         p = f"log_assignment.{i}."
@@ -121,12 +141,13 @@ def make_state_dict(
         sd[p + "weight"], sd[p + "bias"] = _linear(g, 1, d)
         if adaptive:
             sd[p + "weight"] *= 8.0
-            sd[p + "bias"].fill_(1.0 + 1.0 * i)
+            sd[p + "bias"].fill_(0.8 * i)
     return sd
 
 
-def checksum(t: torch.Tensor) -> float:
-    """Order-sensitive fp64 checksum used to pin regenerated tensors to the golden fixtures."""
-    x = t.detach().double().flatten()
-    wts = torch.arange(1, x.numel() + 1, dtype=torch.float64) % 977 + 1.0
-    return float((x * wts).sum())
+def checksum(t: torch.Tensor) -> int:
+    """Order-sensitive, exactly reproducible checksum (int64 arithmetic on the fp32 bit patterns) used
+    to pin regenerated tensors to the golden fixtures."""
+    bits = t.detach().to(torch.float32).contiguous().flatten().view(torch.int32).to(torch.int64)
+    wts = torch.arange(1, bits.numel() + 1, dtype=torch.int64) % 977 + 1
+    return int((bits * wts).sum())
