@@ -1,8 +1,271 @@
-// Attention for the tensor-core path.  (interim: CUDA-core kernel on the fp16 operands; the
-// tcgen05 kernel replaces it behind the same entry point.)
+// tcgen05 flash attention for the tensor-core path (lightglue.py:113-137: softmax(q k^T / 8) v, no mask).
+//
+// One CTA owns 256 query rows (two 128-row tiles) of one (sequence, head) and sweeps the key/value
+// sequence in blocks of 128:
+//   S_t = Q_t K_j^T      tcgen05.mma  M=128 N=128 K=64   operands in shared memory (TMA, 128B swizzle)
+//   P_t = exp2(c S_t - c m_t)   softmax warpgroup t: TMEM -> registers -> fp16 -> TMEM
+//   O_t += P_t V_j       tcgen05.mma  M=128 N=64  K=128  A = P_t from TMEM, B = V^T tile in shared memory
+// The two query tiles ping-pong: while warpgroup 0 runs the softmax of S_0 the tensor core computes
+// P_1 V and S_1 of the next block, and vice versa.  O(N) softmax: running max with lazy rescaling (O is
+// only rescaled when the row max grows by more than 2^8), running sum in fp32, one division at the end.
+// TMEM map (512 columns): S0 0-127 | S1 128-255 | O0 256-319 | O1 320-383 | P0 384-447 | P1 448-511.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-5 softmax
+// warpgroup 0, warps 6-9 softmax warpgroup 1 (one query row per thread; warp w reads TMEM lanes 32*(w%4)..).
+#include <stdlib.h>
+
 #include "lg_handle.h"
+#include "tc_common.cuh"
+
+using namespace tc;
 
 namespace {
+
+constexpr int QT = 128;          // query rows per tile
+constexpr int KB = 128;          // keys per block
+constexpr int KV_STAGES = 4;
+constexpr int Q_TILE_BYTES = QT * 64 * 2;   // 16 KB
+constexpr int K_TILE_BYTES = KB * 64 * 2;   // 16 KB
+constexpr int V_HALF_BYTES = 64 * 64 * 2;   // 8 KB: [64 d rows][64 keys]
+constexpr int KV_STAGE_BYTES = K_TILE_BYTES + 2 * V_HALF_BYTES;  // 32 KB
+constexpr uint32_t TM_S = 0, TM_O = 256, TM_P = 384;
+constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;  // dh^-0.5 * log2(e)
+
+struct AttnParams {
+  CUtensorMap q_map;   // (64, Lp, S*H)   box (64, 128, 1)
+  CUtensorMap k_map;   // (64, Lp, S*H)   box (64, 128, 1)
+  CUtensorMap vt_map;  // (Lp, 64, S*H)   box (64, 64, 1)
+  __nv_bfloat16* ctxh; __nv_bfloat16* ctxl;
+  int kv_shift;
+  SeqState st;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(320, 1) tc_attention_kernel(const __grid_constant__ AttnParams p) {
+  const int s = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * 2 * QT;
+  const int len_q = p.st.len[s];
+  if (r0 >= len_q || lg_pair_stopped(p.st, s)) return;
+  const int skv = (s + p.kv_shift) % p.st.S;
+  const int len_kv = p.st.len[skv];
+  const int nkv = (len_kv + KB - 1) / KB;
+  const int nt = (len_q - r0 > QT) ? 2 : 1;  // live query tiles in this CTA
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sq = smem;                                  // 2 x 16 KB
+  uint8_t* skvb = smem + 2 * Q_TILE_BYTES;             // KV_STAGES x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(skvb + KV_STAGES * KV_STAGE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + KV_STAGES;
+  uint64_t* s_full = kv_empty + KV_STAGES;   // [2]
+  uint64_t* p_full = s_full + 2;             // [2]
+  uint64_t* o_done = p_full + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.q_map);
+    tma_prefetch_desc(&p.k_map);
+    tma_prefetch_desc(&p.vt_map);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128); mbar_init(&o_done[t], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nkv > 0) {
+    if (warp == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, 2 * Q_TILE_BYTES);
+        tma_load_3d(sq, &p.q_map, 0, r0, s * LG_HEADS + h, q_full);
+        tma_load_3d(sq + Q_TILE_BYTES, &p.q_map, 0, r0 + QT, s * LG_HEADS + h, q_full);
+        for (int j = 0; j < nkv; ++j) {
+          const int stage = j % KV_STAGES, round = j / KV_STAGES;
+          mbar_wait(&kv_empty[stage], (round & 1) ^ 1);
+          uint8_t* dst = skvb + stage * KV_STAGE_BYTES;
+          mbar_arrive_expect_tx(&kv_full[stage], KV_STAGE_BYTES);
+          tma_load_3d(dst, &p.k_map, 0, j * KB, skv * LG_HEADS + h, &kv_full[stage]);
+          tma_load_3d(dst + K_TILE_BYTES, &p.vt_map, j * KB, 0, skv * LG_HEADS + h, &kv_full[stage]);
+          tma_load_3d(dst + K_TILE_BYTES + V_HALF_BYTES, &p.vt_map, j * KB + 64, 0, skv * LG_HEADS + h, &kv_full[stage]);
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc_qk = make_idesc(QT, KB, false);  // M=128 N=128, fp16
+      constexpr uint32_t idesc_pv = make_idesc(QT, 64, false);  // M=128 N=64,  fp16
+      auto issue_qk = [&](int t, int stage) {
+        const uint64_t adesc = make_sdesc_sw128(smem_u32(sq + t * Q_TILE_BYTES));
+        const uint64_t bdesc = make_sdesc_sw128(smem_u32(skvb + stage * KV_STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_ss(tmem_base + TM_S + t * 128, sdesc_advance_k(adesc, k * 16), sdesc_advance_k(bdesc, k * 16), idesc_qk,
+                 k > 0 ? 1u : 0u);
+        mma_commit(&s_full[t]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      if (lane == 0)
+        for (int t = 0; t < nt; ++t) issue_qk(t, 0);
+      __syncwarp();
+      for (int j = 0; j < nkv; ++j) {
+        const int stage = j % KV_STAGES;
+        for (int t = 0; t < nt; ++t) {
+          mbar_wait(&p_full[t], j & 1);
+          if (t == 0 && j + 1 < nkv) mbar_wait(&kv_full[(j + 1) % KV_STAGES], ((j + 1) / KV_STAGES) & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t vbase = smem_u32(skvb + stage * KV_STAGE_BYTES + K_TILE_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {  // 8 x 16 keys
+              const uint64_t bdesc = sdesc_advance_k(make_sdesc_sw128(vbase + (ks / 4) * V_HALF_BYTES), (ks % 4) * 16);
+              mma_ts(tmem_base + TM_O + t * 64, tmem_base + TM_P + t * 64 + ks * 8, bdesc, idesc_pv,
+                     (j > 0 || ks > 0) ? 1u : 0u);
+            }
+            if (t == nt - 1) mma_commit(&kv_empty[stage]);  // K_j / V_j fully consumed
+            if (j + 1 < nkv) issue_qk(t, (j + 1) % KV_STAGES);
+            else mma_commit(&o_done[t]);
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+      // ------------------------------------------------------------------ softmax warpgroups
+      const int t = (warp - 2) / 4;
+      if (t < nt) {
+        const int quarter = warp % 4;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        const uint32_t ts = tmem_base + lane_off + TM_S + t * 128;
+        const uint32_t tp = tmem_base + lane_off + TM_P + t * 64;
+        const uint32_t to = tmem_base + lane_off + TM_O + t * 64;
+        float m_used = -INFINITY, l = 0.f;
+        uint32_t raw[32];
+        for (int j = 0; j < nkv; ++j) {
+          mbar_wait(&s_full[t], j & 1);
+          tc_fence_after();
+          const int valid = len_kv - j * KB;  // columns >= valid are padding
+          float mx = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            tmem_ld32(ts + c * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float v = __uint_as_float(raw[i]);
+              mx = fmaxf(mx, (c * 32 + i < valid) ? v : -INFINITY);
+            }
+          }
+          // lazy rescale: keep the old reference max unless the new one exceeds it by > 2^8
+          float alpha = 1.f;
+          bool need = false;
+          if (mx > m_used) {
+            if (m_used == -INFINITY) { m_used = mx; }
+            else if ((mx - m_used) * SCALE_LOG2 > 8.f) { alpha = ex2((m_used - mx) * SCALE_LOG2); m_used = mx; need = true; }
+          }
+          if (__any_sync(0xffffffffu, need)) {  // PV of block j-1 has completed (it precedes S_t(j) in issue order)
+            uint32_t o32[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              tmem_ld32(to + c * 32, o32);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o32[i] = __float_as_uint(__uint_as_float(o32[i]) * alpha);
+              tmem_st32(to + c * 32, o32);
+            }
+            l *= alpha;
+          }
+          const float mc = m_used * SCALE_LOG2;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            tmem_ld32(ts + c * 32, raw);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = (c * 32 + 2 * i < valid) ? ex2(fmaf(__uint_as_float(raw[2 * i]), SCALE_LOG2, -mc)) : 0.f;
+              const float p1 = (c * 32 + 2 * i + 1 < valid) ? ex2(fmaf(__uint_as_float(raw[2 * i + 1]), SCALE_LOG2, -mc)) : 0.f;
+              l += p0 + p1;
+              const __half2 hh = __floats2half2_rn(p0, p1);
+              pk[i] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            tmem_st16(tp + c * 16, pk);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_full[t]);
+        }
+        // ---- epilogue: O / l -> ctx (heads concatenated h-major, lightglue.py:171)
+        mbar_wait(&o_done[t], 0);
+        tc_fence_after();
+        const int r = r0 + t * QT + row;
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        const long off = ((long)s * p.st.Lp + r) * LG_DIM + h * LG_HDIM;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld32(to + c * 32, raw);
+          tmem_ld_wait();
+          if (r < len_q) {
+            uint32_t ph[16], pl[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a = __uint_as_float(raw[2 * i]) * inv, b = __uint_as_float(raw[2 * i + 1]) * inv;
+              const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+              ph[i] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+              const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha));
+              const __nv_bfloat16 lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+              pl[i] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              reinterpret_cast<uint4*>(p.ctxh + off + c * 32)[i] = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
+              if (p.ctxl)
+                reinterpret_cast<uint4*>(p.ctxl + off + c * 32)[i] = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= 2) {
+    // no keys: zeros (lightglue.py:114-115)
+    const int t = (warp - 2) / 4;
+    const int r = r0 + t * QT + (warp % 4) * 32 + lane;
+    if (r < len_q) {
+      const long off = ((long)s * p.st.Lp + r) * LG_DIM + h * LG_HDIM;
+      for (int i = 0; i < 8; ++i) {
+        reinterpret_cast<uint4*>(p.ctxh + off)[i] = make_uint4(0, 0, 0, 0);
+        if (p.ctxl) reinterpret_cast<uint4*>(p.ctxl + off)[i] = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core reference kernel on the same fp16 operands (debug comparator: LG_TC_ATTN_REF=1)
+// ------------------------------------------------------------------------------------------------
 #define AT 64
 #define ALD 65
 __global__ void __launch_bounds__(256) attn_ref_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
@@ -117,19 +380,54 @@ __global__ void __launch_bounds__(256) attn_ref_kernel(const __half* __restrict_
     }
   }
 }
+
+struct AttnMapCache {
+  const void* q; const void* k; const void* vt; int S, Lp;
+  CUtensorMap qm, km, vm;
+};
 }  // namespace
 
 int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shift, const __half* kbuf, cudaStream_t stream) {
-  const size_t smem = (2 * AT * ALD + AT * 64) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
-    attr_set = true;
-  }
-  dim3 grid(st.Lp / AT, LG_HEADS, st.S);
-  attn_ref_kernel<<<grid, 256, smem, stream>>>(b.q, kbuf, b.vt, b.ctxh, b.ctxl, kv_shift, st);
-  LG_CHECK_LAUNCH();
+  static const bool use_ref = getenv("LG_TC_ATTN_REF") && atoi(getenv("LG_TC_ATTN_REF")) != 0;
   h->launches += 1;
+  if (use_ref) {
+    const size_t smem = (2 * AT * ALD + AT * 64) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(attn_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
+      attr_set = true;
+    }
+    attn_ref_kernel<<<dim3(st.Lp / AT, LG_HEADS, st.S), 256, smem, stream>>>(b.q, kbuf, b.vt, b.ctxh, b.ctxl, kv_shift, st);
+    LG_CHECK_LAUNCH();
+    return 0;
+  }
+  // tensor maps depend only on (buffers, S, Lp): cache the last two sets (self: k = b.k, cross: k = b.q)
+  static thread_local AttnMapCache cache[2];
+  AttnMapCache* c = nullptr;
+  for (auto& e : cache)
+    if (e.q == b.q && e.k == kbuf && e.vt == b.vt && e.S == st.S && e.Lp == st.Lp) c = &e;
+  if (!c) {
+    c = &cache[kbuf == b.q ? 1 : 0];
+    const uint64_t SH = (uint64_t)st.S * LG_HEADS, Lp = st.Lp;
+    int r;
+    if ((r = tc_make_tmap_3d(&c->qm, b.q, 2, 64, Lp, SH, 128, Lp * 128, 64, QT, 1))) return r;
+    if ((r = tc_make_tmap_3d(&c->km, kbuf, 2, 64, Lp, SH, 128, Lp * 128, 64, KB, 1))) return r;
+    if ((r = tc_make_tmap_3d(&c->vm, b.vt, 2, Lp, 64, SH, Lp * 2, 64 * Lp * 2, 64, 64, 1))) return r;
+    c->q = b.q; c->k = kbuf; c->vt = b.vt; c->S = st.S; c->Lp = st.Lp;
+  }
+  AttnParams p;
+  p.q_map = c->qm; p.k_map = c->km; p.vt_map = c->vm;
+  p.ctxh = b.ctxh; p.ctxl = b.ctxl; p.kv_shift = kv_shift; p.st = st;
+  constexpr int smem = 2 * Q_TILE_BYTES + KV_STAGES * KV_STAGE_BYTES + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
+    attr = true;
+  }
+  dim3 grid((st.Lp + 2 * QT - 1) / (2 * QT), LG_HEADS, st.S);
+  tc_attention_kernel<<<grid, 320, smem, stream>>>(p);
+  LG_CHECK_LAUNCH();
   return 0;
 }
