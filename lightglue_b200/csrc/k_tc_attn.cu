@@ -3,12 +3,16 @@
 // One CTA owns 256 query rows (two 128-row tiles) of one (sequence, head) and sweeps the key/value
 // sequence in blocks of 128:
 //   S_t = Q_t K_j^T      tcgen05.mma  M=128 N=128 K=64   operands in shared memory (TMA, 128B swizzle)
-//   P_t = exp2(c S_t - c m_t)   softmax warpgroup t: TMEM -> registers -> fp16 -> TMEM
-//   O_t += P_t V_j       tcgen05.mma  M=128 N=64  K=128  A = P_t from TMEM, B = V^T tile in shared memory
+//   P_t = exp2(c S_t - c m_t)   softmax warpgroup t: TMEM -> registers -> fp16 -> TMEM (in place over S_t)
+//   O_t += P_t [V_j | 1] tcgen05.mma  M=128 N=80  K=128  A = P_t from TMEM, B = V^T tile in shared memory
+//                        extended by a constant row of ones: column 64 of O_t is the softmax denominator,
+//                        accumulated by the tensor core from the same fp16 P the numerator uses.
 // The two query tiles ping-pong: while warpgroup 0 runs the softmax of S_0 the tensor core computes
 // P_1 V and S_1 of the next block, and vice versa.  O(N) softmax: running max with lazy rescaling (O is
-// only rescaled when the row max grows by more than 2^8), running sum in fp32, one division at the end.
-// TMEM map (512 columns): S0 0-127 | S1 128-255 | O0 256-319 | O1 320-383 | P0 384-447 | P1 448-511.
+// only rescaled when the row max grows by more than 2^8), one division at the end.
+// FAST (LG_PREC_BF16): exponentials are evaluated two at a time with ex2.approx.f16x2 on
+// (s - m) * c computed in fp32 -- the result is directly the packed fp16 P operand; halves MUFU work.
+// TMEM map (512 columns): S0/P0 0-127 | S1/P1 128-255 | O0 256-335 | O1 384-463.
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-5 softmax
 // warpgroup 0, warps 6-9 softmax warpgroup 1 (one query row per thread; warp w reads TMEM lanes 32*(w%4)..).
 #include <stdlib.h>
@@ -25,9 +29,11 @@ constexpr int KB = 128;          // keys per block
 constexpr int KV_STAGES = 4;
 constexpr int Q_TILE_BYTES = QT * 64 * 2;   // 16 KB
 constexpr int K_TILE_BYTES = KB * 64 * 2;   // 16 KB
-constexpr int V_HALF_BYTES = 64 * 64 * 2;   // 8 KB: [64 d rows][64 keys]
-constexpr int KV_STAGE_BYTES = K_TILE_BYTES + 2 * V_HALF_BYTES;  // 32 KB
-constexpr uint32_t TM_S = 0, TM_O = 256, TM_P = 384;
+constexpr int V_ROWS = 80;                  // 64 value channels + the ones row + 15 zero rows (N % 16 == 0)
+constexpr int V_HALF_BYTES = V_ROWS * 128;  // 10 KB: [80 rows][64 keys]
+constexpr int KV_STAGE_BYTES = K_TILE_BYTES + 2 * V_HALF_BYTES;  // 36 KB
+constexpr int V_TMA_BYTES = 64 * 128;       // bytes TMA writes per half
+constexpr uint32_t TM_S = 0, TM_O = 256;
 constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;  // dh^-0.5 * log2(e)
 
 struct AttnParams {
@@ -44,6 +50,17 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ uint32_t ex2_f16x2(float x0, float x1) {  // {2^x0, 2^x1} as packed fp16 (x0 in the low half)
+  uint32_t h, y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(h));
+  return y;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -53,6 +70,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(320, 1) tc_attention_kernel(const __grid_constant__ AttnParams p) {
   const int s = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * 2 * QT;
   const int len_q = p.st.len[s];
@@ -65,7 +83,7 @@ __global__ void __launch_bounds__(320, 1) tc_attention_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sq = smem;                                  // 2 x 16 KB
-  uint8_t* skvb = smem + 2 * Q_TILE_BYTES;             // KV_STAGES x 32 KB
+  uint8_t* skvb = smem + 2 * Q_TILE_BYTES;             // KV_STAGES x 36 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(skvb + KV_STAGES * KV_STAGE_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
@@ -77,6 +95,14 @@ __global__ void __launch_bounds__(320, 1) tc_attention_kernel(const __grid_const
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
+  // constant rows 64..79 of every V^T half tile: row 64 = ones (fp16), rows 65..79 = zeros
+  for (int e = threadIdx.x; e < KV_STAGES * 2 * (16 * 128 / 16); e += blockDim.x) {
+    const int tile = e / 128, w = e % 128;  // 128 x 16-byte words per constant region
+    uint8_t* base = skvb + (tile / 2) * KV_STAGE_BYTES + K_TILE_BYTES + (tile % 2) * V_HALF_BYTES + V_TMA_BYTES;
+    const uint32_t v = (w < 8) ? 0x3C003C00u : 0u;
+    reinterpret_cast<uint4*>(base)[w] = make_uint4(v, v, v, v);
+  }
+  fence_proxy_async();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.q_map);
     tma_prefetch_desc(&p.k_map);
@@ -103,7 +129,7 @@ __global__ void __launch_bounds__(320, 1) tc_attention_kernel(const __grid_const
           const int stage = j % KV_STAGES, round = j / KV_STAGES;
           mbar_wait(&kv_empty[stage], (round & 1) ^ 1);
           uint8_t* dst = skvb + stage * KV_STAGE_BYTES;
-          mbar_arrive_expect_tx(&kv_full[stage], KV_STAGE_BYTES);
+          mbar_arrive_expect_tx(&kv_full[stage], K_TILE_BYTES + 2 * V_TMA_BYTES);
           tma_load_3d(dst, &p.k_map, 0, j * KB, skv * LG_HEADS + h, &kv_full[stage]);
           tma_load_3d(dst + K_TILE_BYTES, &p.vt_map, j * KB, 0, skv * LG_HEADS + h, &kv_full[stage]);
           tma_load_3d(dst + K_TILE_BYTES + V_HALF_BYTES, &p.vt_map, j * KB + 64, 0, skv * LG_HEADS + h, &kv_full[stage]);
@@ -111,8 +137,8 @@ __global__ void __launch_bounds__(320, 1) tc_attention_kernel(const __grid_const
       }
     } else if (warp == 1) {
       // ------------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc_qk = make_idesc(QT, KB, false);  // M=128 N=128, fp16
-      constexpr uint32_t idesc_pv = make_idesc(QT, 64, false);  // M=128 N=64,  fp16
+      constexpr uint32_t idesc_qk = make_idesc(QT, KB, false);      // M=128 N=128, fp16
+      constexpr uint32_t idesc_pv = make_idesc(QT, V_ROWS, false);  // M=128 N=80,  fp16
       auto issue_qk = [&](int t, int stage) {
         const uint64_t adesc = make_sdesc_sw128(smem_u32(sq + t * Q_TILE_BYTES));
         const uint64_t bdesc = make_sdesc_sw128(smem_u32(skvb + stage * KV_STAGE_BYTES));
@@ -137,12 +163,13 @@ __global__ void __launch_bounds__(320, 1) tc_attention_kernel(const __grid_const
           if (lane == 0) {
             const uint32_t vbase = smem_u32(skvb + stage * KV_STAGE_BYTES + K_TILE_BYTES);
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {  // 8 x 16 keys
+            for (int ks = 0; ks < 8; ++ks) {  // 8 x 16 keys; P_t lives in the first 64 columns of S_t
               const uint64_t bdesc = sdesc_advance_k(make_sdesc_sw128(vbase + (ks / 4) * V_HALF_BYTES), (ks % 4) * 16);
-              mma_ts(tmem_base + TM_O + t * 64, tmem_base + TM_P + t * 64 + ks * 8, bdesc, idesc_pv,
+              mma_ts(tmem_base + TM_O + t * 128, tmem_base + TM_S + t * 128 + ks * 8, bdesc, idesc_pv,
                      (j > 0 || ks > 0) ? 1u : 0u);
             }
             if (t == nt - 1) mma_commit(&kv_empty[stage]);  // K_j / V_j fully consumed
+            // the tensor pipe executes in issue order, so S_t(j+1) cannot overwrite P_t(j) before P_t V is done
             if (j + 1 < nkv) issue_qk(t, (j + 1) % KV_STAGES);
             else mma_commit(&o_done[t]);
           }
@@ -157,24 +184,30 @@ __global__ void __launch_bounds__(320, 1) tc_attention_kernel(const __grid_const
         const int row = quarter * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
         const uint32_t ts = tmem_base + lane_off + TM_S + t * 128;
-        const uint32_t tp = tmem_base + lane_off + TM_P + t * 64;
-        const uint32_t to = tmem_base + lane_off + TM_O + t * 64;
-        float m_used = -INFINITY, l = 0.f;
-        uint32_t raw[32];
+        const uint32_t to = tmem_base + lane_off + TM_O + t * 128;
+        float m_used = -INFINITY;
+        uint32_t ra[32], rb[32];
         for (int j = 0; j < nkv; ++j) {
           mbar_wait(&s_full[t], j & 1);
           tc_fence_after();
-          const int valid = len_kv - j * KB;  // columns >= valid are padding
+          const int valid = len_kv - j * KB;  // columns >= valid are padding (last block only)
+          const bool full = valid >= KB;
+          // ---- sweep 1: row max
           float mx = -INFINITY;
+          tmem_ld32(ts, ra);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            tmem_ld32(ts + c * 32, raw);
+            uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+            uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
             tmem_ld_wait();
+            if (c < 3) tmem_ld32(ts + (c + 1) * 32, nxt);
+            if (!full) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float v = __uint_as_float(raw[i]);
-              mx = fmaxf(mx, (c * 32 + i < valid) ? v : -INFINITY);
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i >= valid) cur[i] = 0xff800000u;  // -inf
             }
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
           }
           // lazy rescale: keep the old reference max unless the new one exceeds it by > 2^8
           float alpha = 1.f;
@@ -183,7 +216,8 @@ __global__ void __launch_bounds__(320, 1) tc_attention_kernel(const __grid_const
             if (m_used == -INFINITY) { m_used = mx; }
             else if ((mx - m_used) * SCALE_LOG2 > 8.f) { alpha = ex2((m_used - mx) * SCALE_LOG2); m_used = mx; need = true; }
           }
-          if (__any_sync(0xffffffffu, need)) {  // PV of block j-1 has completed (it precedes S_t(j) in issue order)
+          tmem_ld32(ts, ra);  // start sweep 2's first load under the rescale decision
+          if (__any_sync(0xffffffffu, need)) {  // P_t V of block j-1 has completed (it precedes S_t(j) in issue order)
             uint32_t o32[32];
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -193,43 +227,62 @@ __global__ void __launch_bounds__(320, 1) tc_attention_kernel(const __grid_const
               for (int i = 0; i < 32; ++i) o32[i] = __float_as_uint(__uint_as_float(o32[i]) * alpha);
               tmem_st32(to + c * 32, o32);
             }
-            l *= alpha;
+            uint32_t o16[16];
+            tmem_ld16(to + 64, o16);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o16[i] = __float_as_uint(__uint_as_float(o16[i]) * alpha);
+            tmem_st16(to + 64, o16);
           }
+          // ---- sweep 2: P = exp2(c s - c m) as fp16, written over the first 64 columns of S_t
           const float mc = m_used * SCALE_LOG2;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            tmem_ld32(ts + c * 32, raw);
+            uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+            uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
             tmem_ld_wait();
+            if (c < 3) tmem_ld32(ts + (c + 1) * 32, nxt);
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float p0 = (c * 32 + 2 * i < valid) ? ex2(fmaf(__uint_as_float(raw[2 * i]), SCALE_LOG2, -mc)) : 0.f;
-              const float p1 = (c * 32 + 2 * i + 1 < valid) ? ex2(fmaf(__uint_as_float(raw[2 * i + 1]), SCALE_LOG2, -mc)) : 0.f;
-              l += p0 + p1;
-              const __half2 hh = __floats2half2_rn(p0, p1);
-              pk[i] = *reinterpret_cast<const uint32_t*>(&hh);
+              float x0 = fmaf(__uint_as_float(cur[2 * i]), SCALE_LOG2, -mc);
+              float x1 = fmaf(__uint_as_float(cur[2 * i + 1]), SCALE_LOG2, -mc);
+              if (!full) {
+                if (c * 32 + 2 * i >= valid) x0 = -INFINITY;
+                if (c * 32 + 2 * i + 1 >= valid) x1 = -INFINITY;
+              }
+              if (FAST) {
+                pk[i] = ex2_f16x2(x0, x1);
+              } else {
+                const __half2 hh = __floats2half2_rn(ex2(x0), ex2(x1));
+                pk[i] = *reinterpret_cast<const uint32_t*>(&hh);
+              }
             }
-            tmem_st16(tp + c * 16, pk);
+            tmem_st16(ts + c * 16, pk);
           }
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&p_full[t]);
         }
-        // ---- epilogue: O / l -> ctx (heads concatenated h-major, lightglue.py:171)
+        // ---- epilogue: O[:, 0:64] / O[:, 64] -> ctx (heads concatenated h-major, lightglue.py:171)
         mbar_wait(&o_done[t], 0);
         tc_fence_after();
         const int r = r0 + t * QT + row;
+        uint32_t o16[16];
+        tmem_ld16(to + 64, o16);
+        tmem_ld_wait();
+        const float l = __uint_as_float(o16[0]);
         const float inv = l > 0.f ? 1.f / l : 0.f;
         const long off = ((long)s * p.st.Lp + r) * LG_DIM + h * LG_HDIM;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          tmem_ld32(to + c * 32, raw);
+          tmem_ld32(to + c * 32, ra);
           tmem_ld_wait();
           if (r < len_q) {
             uint32_t ph[16], pl[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float a = __uint_as_float(raw[2 * i]) * inv, b = __uint_as_float(raw[2 * i + 1]) * inv;
+              const float a = __uint_as_float(ra[2 * i]) * inv, b = __uint_as_float(ra[2 * i + 1]) * inv;
               const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
               ph[i] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
               const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha));
@@ -422,12 +475,15 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
   constexpr int smem = 2 * Q_TILE_BYTES + KV_STAGES * KV_STAGE_BYTES + 1024 + 256;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
     attr = true;
   }
   dim3 grid((st.Lp + 2 * QT - 1) / (2 * QT), LG_HEADS, st.S);
-  tc_attention_kernel<<<grid, 320, smem, stream>>>(p);
+  if (h->cfg.precision == LG_PREC_BF16) tc_attention_kernel<true><<<grid, 320, smem, stream>>>(p);
+  else tc_attention_kernel<false><<<grid, 320, smem, stream>>>(p);
   LG_CHECK_LAUNCH();
   return 0;
 }
