@@ -71,7 +71,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(320, 1) tc_attention_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __maxnreg__(200) tc_attention_kernel(const __grid_constant__ AttnParams p) {
   const int s = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * 2 * QT;
   const int len_q = p.st.len[s];
   if (r0 >= len_q || lg_pair_stopped(p.st, s)) return;
@@ -186,29 +186,30 @@ __global__ void __launch_bounds__(320, 1) tc_attention_kernel(const __grid_const
         const uint32_t ts = tmem_base + lane_off + TM_S + t * 128;
         const uint32_t to = tmem_base + lane_off + TM_O + t * 128;
         float m_used = -INFINITY;
-        uint32_t ra[32], rb[32];
+        uint32_t sv[4][32];  // the whole 128-column S row of this thread: TMEM is read exactly once per block
         for (int j = 0; j < nkv; ++j) {
           mbar_wait(&s_full[t], j & 1);
           tc_fence_after();
           const int valid = len_kv - j * KB;  // columns >= valid are padding (last block only)
-          const bool full = valid >= KB;
-          // ---- sweep 1: row max
-          float mx = -INFINITY;
-          tmem_ld32(ts, ra);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t (&cur)[32] = (c & 1) ? rb : ra;
-            uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
-            tmem_ld_wait();
-            if (c < 3) tmem_ld32(ts + (c + 1) * 32, nxt);
-            if (!full) {
+          for (int c = 0; c < 4; ++c) tmem_ld32(ts + c * 32, sv[c]);
+          tmem_ld_wait();
+          if (valid < KB) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (c * 32 + i >= valid) cur[i] = 0xff800000u;  // -inf
-            }
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
+                if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;  // -inf
           }
+          float mx0 = -INFINITY, mx1 = -INFINITY;  // two chains for ILP
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              mx0 = max3(mx0, __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+              mx1 = max3(mx1, __uint_as_float(sv[c][i + 2]), __uint_as_float(sv[c][i + 3]));
+            }
+          const float mx = fmaxf(mx0, mx1);
           // lazy rescale: keep the old reference max unless the new one exceeds it by > 2^8
           float alpha = 1.f;
           bool need = false;
@@ -216,7 +217,6 @@ __global__ void __launch_bounds__(320, 1) tc_attention_kernel(const __grid_const
             if (m_used == -INFINITY) { m_used = mx; }
             else if ((mx - m_used) * SCALE_LOG2 > 8.f) { alpha = ex2((m_used - mx) * SCALE_LOG2); m_used = mx; need = true; }
           }
-          tmem_ld32(ts, ra);  // start sweep 2's first load under the rescale decision
           if (__any_sync(0xffffffffu, need)) {  // P_t V of block j-1 has completed (it precedes S_t(j) in issue order)
             uint32_t o32[32];
 #pragma unroll
@@ -234,23 +234,15 @@ __global__ void __launch_bounds__(320, 1) tc_attention_kernel(const __grid_const
             for (int i = 0; i < 16; ++i) o16[i] = __float_as_uint(__uint_as_float(o16[i]) * alpha);
             tmem_st16(to + 64, o16);
           }
-          // ---- sweep 2: P = exp2(c s - c m) as fp16, written over the first 64 columns of S_t
+          // P = exp2(c s - c m) as fp16, written over the first 64 columns of S_t
           const float mc = m_used * SCALE_LOG2;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            uint32_t (&cur)[32] = (c & 1) ? rb : ra;
-            uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
-            tmem_ld_wait();
-            if (c < 3) tmem_ld32(ts + (c + 1) * 32, nxt);
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              float x0 = fmaf(__uint_as_float(cur[2 * i]), SCALE_LOG2, -mc);
-              float x1 = fmaf(__uint_as_float(cur[2 * i + 1]), SCALE_LOG2, -mc);
-              if (!full) {
-                if (c * 32 + 2 * i >= valid) x0 = -INFINITY;
-                if (c * 32 + 2 * i + 1 >= valid) x1 = -INFINITY;
-              }
+              const float x0 = fmaf(__uint_as_float(sv[c][2 * i]), SCALE_LOG2, -mc);
+              const float x1 = fmaf(__uint_as_float(sv[c][2 * i + 1]), SCALE_LOG2, -mc);
               if (FAST) {
                 pk[i] = ex2_f16x2(x0, x1);
               } else {
@@ -276,13 +268,13 @@ __global__ void __launch_bounds__(320, 1) tc_attention_kernel(const __grid_const
         const long off = ((long)s * p.st.Lp + r) * LG_DIM + h * LG_HDIM;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          tmem_ld32(to + c * 32, ra);
+          tmem_ld32(to + c * 32, sv[c]);
           tmem_ld_wait();
           if (r < len_q) {
             uint32_t ph[16], pl[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float a = __uint_as_float(ra[2 * i]) * inv, b = __uint_as_float(ra[2 * i + 1]) * inv;
+              const float a = __uint_as_float(sv[c][2 * i]) * inv, b = __uint_as_float(sv[c][2 * i + 1]) * inv;
               const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
               ph[i] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
               const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha));
