@@ -13,8 +13,10 @@
 // FAST (LG_PREC_BF16): exponentials are evaluated two at a time with ex2.approx.f16x2 on
 // (s - m) * c computed in fp32 -- the result is directly the packed fp16 P operand; halves MUFU work.
 // TMEM map (512 columns): S0/P0 0-127 | S1/P1 128-255 | O0 256-335 | O1 384-463.
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-5 softmax
-// warpgroup 0, warps 6-9 softmax warpgroup 1 (one query row per thread; warp w reads TMEM lanes 32*(w%4)..).
+// Warp roles (384 threads = 3 warpgroups): warpgroup 0 = {warp 0 TMA producer, warp 1 TMEM owner + MMA
+// issuer, 2 idle warps} shrinks to 56 registers (setmaxnreg.dec); warpgroups 1 and 2 are the softmax
+// warpgroups of query tile 0 / 1 and grow to 216 registers: each thread keeps its whole 128-column S row
+// in registers so that TMEM is read once per block (one query row per thread; warp w reads TMEM lanes 32*(w%4)..).
 #include <stdlib.h>
 
 #include "lg_handle.h"
@@ -71,7 +73,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 
 template <bool FAST>
-__global__ void __maxnreg__(200) tc_attention_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_constant__ AttnParams p) {
   const int s = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * 2 * QT;
   const int len_q = p.st.len[s];
   if (r0 >= len_q || lg_pair_stopped(p.st, s)) return;
@@ -118,7 +120,9 @@ __global__ void __maxnreg__(200) tc_attention_kernel(const __grid_constant__ Att
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (nkv > 0) {
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (nkv > 0) {
     if (warp == 0) {
       // ------------------------------------------------------------------ TMA producer
       if (lane == 0) {
@@ -176,9 +180,13 @@ __global__ void __maxnreg__(200) tc_attention_kernel(const __grid_constant__ Att
           __syncwarp();
         }
       }
-    } else {
+    }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    if (nkv > 0) {
       // ------------------------------------------------------------------ softmax warpgroups
-      const int t = (warp - 2) / 4;
+      const int t = (warp - 4) / 4;
       if (t < nt) {
         const int quarter = warp % 4;
         const int row = quarter * 32 + lane;
@@ -290,10 +298,9 @@ __global__ void __maxnreg__(200) tc_attention_kernel(const __grid_constant__ Att
           }
         }
       }
-    }
-  } else if (warp >= 2) {
+    } else {
     // no keys: zeros (lightglue.py:114-115)
-    const int t = (warp - 2) / 4;
+    const int t = (warp - 4) / 4;
     const int r = r0 + t * QT + (warp % 4) * 32 + lane;
     if (r < len_q) {
       const long off = ((long)s * p.st.Lp + r) * LG_DIM + h * LG_HDIM;
@@ -301,6 +308,7 @@ __global__ void __maxnreg__(200) tc_attention_kernel(const __grid_constant__ Att
         reinterpret_cast<uint4*>(p.ctxh + off)[i] = make_uint4(0, 0, 0, 0);
         if (p.ctxl) reinterpret_cast<uint4*>(p.ctxl + off)[i] = make_uint4(0, 0, 0, 0);
       }
+    }
     }
   }
   tc_fence_before();
@@ -474,8 +482,8 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
     attr = true;
   }
   dim3 grid((st.Lp + 2 * QT - 1) / (2 * QT), LG_HEADS, st.S);
-  if (h->cfg.precision == LG_PREC_BF16) tc_attention_kernel<true><<<grid, 320, smem, stream>>>(p);
-  else tc_attention_kernel<false><<<grid, 320, smem, stream>>>(p);
+  if (h->cfg.precision == LG_PREC_BF16) tc_attention_kernel<true><<<grid, 384, smem, stream>>>(p);
+  else tc_attention_kernel<false><<<grid, 384, smem, stream>>>(p);
   LG_CHECK_LAUNCH();
   return 0;
 }
