@@ -1,22 +1,22 @@
 // tcgen05 flash attention for the tensor-core path (lightglue.py:113-137: softmax(q k^T / 8) v, no mask).
 //
 // One CTA owns 256 query rows (two 128-row tiles) of one (sequence, head) and sweeps the key/value
-// sequence in blocks of 128:
-//   S_t = Q_t K_j^T      tcgen05.mma  M=128 N=128 K=64   operands in shared memory (TMA, 128B swizzle)
+// sequence in blocks of 64:
+//   S_t = Q_t K_j^T      tcgen05.mma  M=128 N=64 K=64    operands in shared memory (TMA, 128B swizzle)
 //   P_t = exp2(c S_t - c m_t)   softmax warpgroup t: TMEM -> registers -> fp16 -> TMEM (in place over S_t)
-//   O_t += P_t [V_j | 1] tcgen05.mma  M=128 N=80  K=128  A = P_t from TMEM, B = V^T tile in shared memory
+//   O_t += P_t [V_j | 1] tcgen05.mma  M=128 N=80 K=64    A = P_t from TMEM, B = V^T tile in shared memory
 //                        extended by a constant row of ones: column 64 of O_t is the softmax denominator,
 //                        accumulated by the tensor core from the same fp16 P the numerator uses.
-// The two query tiles ping-pong: while warpgroup 0 runs the softmax of S_0 the tensor core computes
-// P_1 V and S_1 of the next block, and vice versa.  O(N) softmax: running max with lazy rescaling (O is
-// only rescaled when the row max grows by more than 2^8), one division at the end.
-// FAST (LG_PREC_BF16): exponentials are evaluated two at a time with ex2.approx.f16x2 on
-// (s - m) * c computed in fp32 -- the result is directly the packed fp16 P operand; halves MUFU work.
-// TMEM map (512 columns): S0/P0 0-127 | S1/P1 128-255 | O0 256-335 | O1 384-463.
+// S is double-buffered per query tile: S_t(j+1) is computed while warpgroup t is still busy with the
+// softmax of S_t(j), so the softmax warps (the MUFU pipe is the bound at head_dim 64) never wait for
+// the tensor core.  O(N) softmax: running max with lazy rescaling (O is only rescaled when the row
+// max grows by more than 2^8), one division at the end.
+// FAST (LG_PREC_BF16): exponentials go through ex2.approx.f16x2 on (s - m) * c computed in fp32 -- the
+// result is directly the packed fp16 P operand.
+// TMEM map (512 columns): S[t][b] at 128*t + 64*b (P aliases its first 32 columns) | O0 256-335 | O1 384-463.
 // Warp roles (384 threads = 3 warpgroups): warpgroup 0 = {warp 0 TMA producer, warp 1 TMEM owner + MMA
-// issuer, 2 idle warps} shrinks to 56 registers (setmaxnreg.dec); warpgroups 1 and 2 are the softmax
-// warpgroups of query tile 0 / 1 and grow to 216 registers: each thread keeps its whole 128-column S row
-// in registers so that TMEM is read once per block (one query row per thread; warp w reads TMEM lanes 32*(w%4)..).
+// issuer, 2 idle warps} shrinks its registers (setmaxnreg.dec); warpgroups 1 and 2 are the softmax
+// warpgroups of query tile 0 / 1 (one query row per thread; warp w reads TMEM lanes 32*(w%4)..).
 #include <stdlib.h>
 
 #include "lg_handle.h"
@@ -27,20 +27,20 @@ using namespace tc;
 namespace {
 
 constexpr int QT = 128;          // query rows per tile
-constexpr int KB = 128;          // keys per block
-constexpr int KV_STAGES = 4;
+constexpr int KB = 64;           // keys per block
+constexpr int KV_STAGES = 8;
 constexpr int Q_TILE_BYTES = QT * 64 * 2;   // 16 KB
-constexpr int K_TILE_BYTES = KB * 64 * 2;   // 16 KB
+constexpr int K_TILE_BYTES = KB * 64 * 2;   // 8 KB
 constexpr int V_ROWS = 80;                  // 64 value channels + the ones row + 15 zero rows (N % 16 == 0)
-constexpr int V_HALF_BYTES = V_ROWS * 128;  // 10 KB: [80 rows][64 keys]
-constexpr int KV_STAGE_BYTES = K_TILE_BYTES + 2 * V_HALF_BYTES;  // 36 KB
-constexpr int V_TMA_BYTES = 64 * 128;       // bytes TMA writes per half
+constexpr int V_TILE_BYTES = V_ROWS * 128;  // 10 KB: [80 rows][64 keys]
+constexpr int KV_STAGE_BYTES = K_TILE_BYTES + V_TILE_BYTES;  // 18 KB
+constexpr int V_TMA_BYTES = 64 * 128;       // bytes TMA writes into the V tile
 constexpr uint32_t TM_S = 0, TM_O = 256;
 constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;  // dh^-0.5 * log2(e)
 
 struct AttnParams {
   CUtensorMap q_map;   // (64, Lp, S*H)   box (64, 128, 1)
-  CUtensorMap k_map;   // (64, Lp, S*H)   box (64, 128, 1)
+  CUtensorMap k_map;   // (64, Lp, S*H)   box (64, 64, 1)
   CUtensorMap vt_map;  // (Lp, 64, S*H)   box (64, 64, 1)
   __nv_bfloat16* ctxh; __nv_bfloat16* ctxl;
   int kv_shift;
@@ -85,22 +85,22 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sq = smem;                                  // 2 x 16 KB
-  uint8_t* skvb = smem + 2 * Q_TILE_BYTES;             // KV_STAGES x 36 KB
+  uint8_t* skvb = smem + 2 * Q_TILE_BYTES;             // KV_STAGES x 18 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(skvb + KV_STAGES * KV_STAGE_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + KV_STAGES;
-  uint64_t* s_full = kv_empty + KV_STAGES;   // [2]
-  uint64_t* p_full = s_full + 2;             // [2]
+  uint64_t* s_full = kv_empty + KV_STAGES;   // [t][b] -> s_full[2 * t + b]
+  uint64_t* p_full = s_full + 4;             // [2]
   uint64_t* o_done = p_full + 2;             // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
-  // constant rows 64..79 of every V^T half tile: row 64 = ones (fp16), rows 65..79 = zeros
-  for (int e = threadIdx.x; e < KV_STAGES * 2 * (16 * 128 / 16); e += blockDim.x) {
+  // constant rows 64..79 of every V^T tile: row 64 = ones (fp16), rows 65..79 = zeros
+  for (int e = threadIdx.x; e < KV_STAGES * 128; e += blockDim.x) {
     const int tile = e / 128, w = e % 128;  // 128 x 16-byte words per constant region
-    uint8_t* base = skvb + (tile / 2) * KV_STAGE_BYTES + K_TILE_BYTES + (tile % 2) * V_HALF_BYTES + V_TMA_BYTES;
+    uint8_t* base = skvb + tile * KV_STAGE_BYTES + K_TILE_BYTES + V_TMA_BYTES;
     const uint32_t v = (w < 8) ? 0x3C003C00u : 0u;
     reinterpret_cast<uint4*>(base)[w] = make_uint4(v, v, v, v);
   }
@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
     tma_prefetch_desc(&p.vt_map);
     mbar_init(q_full, 1);
     for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128); mbar_init(&o_done[t], 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(&p_full[t], 128); mbar_init(&o_done[t], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -121,97 +122,101 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (nkv > 0) {
-    if (warp == 0) {
-      // ------------------------------------------------------------------ TMA producer
-      if (lane == 0) {
-        mbar_arrive_expect_tx(q_full, 2 * Q_TILE_BYTES);
-        tma_load_3d(sq, &p.q_map, 0, r0, s * LG_HEADS + h, q_full);
-        tma_load_3d(sq + Q_TILE_BYTES, &p.q_map, 0, r0 + QT, s * LG_HEADS + h, q_full);
-        for (int j = 0; j < nkv; ++j) {
-          const int stage = j % KV_STAGES, round = j / KV_STAGES;
-          mbar_wait(&kv_empty[stage], (round & 1) ^ 1);
-          uint8_t* dst = skvb + stage * KV_STAGE_BYTES;
-          mbar_arrive_expect_tx(&kv_full[stage], K_TILE_BYTES + 2 * V_TMA_BYTES);
-          tma_load_3d(dst, &p.k_map, 0, j * KB, skv * LG_HEADS + h, &kv_full[stage]);
-          tma_load_3d(dst + K_TILE_BYTES, &p.vt_map, j * KB, 0, skv * LG_HEADS + h, &kv_full[stage]);
-          tma_load_3d(dst + K_TILE_BYTES + V_HALF_BYTES, &p.vt_map, j * KB + 64, 0, skv * LG_HEADS + h, &kv_full[stage]);
-        }
-      }
-    } else if (warp == 1) {
-      // ------------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc_qk = make_idesc(QT, KB, false);      // M=128 N=128, fp16
-      constexpr uint32_t idesc_pv = make_idesc(QT, V_ROWS, false);  // M=128 N=80,  fp16
-      auto issue_qk = [&](int t, int stage) {
-        const uint64_t adesc = make_sdesc_sw128(smem_u32(sq + t * Q_TILE_BYTES));
-        const uint64_t bdesc = make_sdesc_sw128(smem_u32(skvb + stage * KV_STAGE_BYTES));
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          mma_ss(tmem_base + TM_S + t * 128, sdesc_advance_k(adesc, k * 16), sdesc_advance_k(bdesc, k * 16), idesc_qk,
-                 k > 0 ? 1u : 0u);
-        mma_commit(&s_full[t]);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      if (lane == 0)
-        for (int t = 0; t < nt; ++t) issue_qk(t, 0);
-      __syncwarp();
-      for (int j = 0; j < nkv; ++j) {
-        const int stage = j % KV_STAGES;
-        for (int t = 0; t < nt; ++t) {
-          mbar_wait(&p_full[t], j & 1);
-          if (t == 0 && j + 1 < nkv) mbar_wait(&kv_full[(j + 1) % KV_STAGES], ((j + 1) / KV_STAGES) & 1);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t vbase = smem_u32(skvb + stage * KV_STAGE_BYTES + K_TILE_BYTES);
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {  // 8 x 16 keys; P_t lives in the first 64 columns of S_t
-              const uint64_t bdesc = sdesc_advance_k(make_sdesc_sw128(vbase + (ks / 4) * V_HALF_BYTES), (ks % 4) * 16);
-              mma_ts(tmem_base + TM_O + t * 128, tmem_base + TM_S + t * 128 + ks * 8, bdesc, idesc_pv,
-                     (j > 0 || ks > 0) ? 1u : 0u);
-            }
-            if (t == nt - 1) mma_commit(&kv_empty[stage]);  // K_j / V_j fully consumed
-            // the tensor pipe executes in issue order, so S_t(j+1) cannot overwrite P_t(j) before P_t V is done
-            if (j + 1 < nkv) issue_qk(t, (j + 1) % KV_STAGES);
-            else mma_commit(&o_done[t]);
+      if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+          mbar_arrive_expect_tx(q_full, 2 * Q_TILE_BYTES);
+          tma_load_3d(sq, &p.q_map, 0, r0, s * LG_HEADS + h, q_full);
+          tma_load_3d(sq + Q_TILE_BYTES, &p.q_map, 0, r0 + QT, s * LG_HEADS + h, q_full);
+          for (int j = 0; j < nkv; ++j) {
+            const int stage = j % KV_STAGES, round = j / KV_STAGES;
+            mbar_wait(&kv_empty[stage], (round & 1) ^ 1);
+            uint8_t* dst = skvb + stage * KV_STAGE_BYTES;
+            mbar_arrive_expect_tx(&kv_full[stage], K_TILE_BYTES + V_TMA_BYTES);
+            tma_load_3d(dst, &p.k_map, 0, j * KB, skv * LG_HEADS + h, &kv_full[stage]);
+            tma_load_3d(dst + K_TILE_BYTES, &p.vt_map, j * KB, 0, skv * LG_HEADS + h, &kv_full[stage]);
           }
+        }
+      } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc_qk = make_idesc(QT, KB, false);      // M=128 N=64, fp16
+        constexpr uint32_t idesc_pv = make_idesc(QT, V_ROWS, false);  // M=128 N=80, fp16
+        auto issue_qk = [&](int t, int j) {  // S[t][j & 1] = Q_t K_j^T
+          const uint64_t adesc = make_sdesc_sw128(smem_u32(sq + t * Q_TILE_BYTES));
+          const uint64_t bdesc = make_sdesc_sw128(smem_u32(skvb + (j % KV_STAGES) * KV_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ss(tmem_base + TM_S + t * 128 + (j & 1) * 64, sdesc_advance_k(adesc, k * 16), sdesc_advance_k(bdesc, k * 16),
+                   idesc_qk, k > 0 ? 1u : 0u);
+          mma_commit(&s_full[2 * t + (j & 1)]);
+        };
+        mbar_wait(q_full, 0);
+        for (int j = 0; j < 2 && j < nkv; ++j) {  // prologue: S_t(0), S_t(1)
+          mbar_wait(&kv_full[j % KV_STAGES], 0);
+          tc_fence_after();
+          if (lane == 0)
+            for (int t = 0; t < nt; ++t) issue_qk(t, j);
           __syncwarp();
         }
+        for (int j = 0; j < nkv; ++j) {
+          const int stage = j % KV_STAGES;
+          if (j + 2 < nkv) mbar_wait(&kv_full[(j + 2) % KV_STAGES], ((j + 2) / KV_STAGES) & 1);
+          for (int t = 0; t < nt; ++t) {
+            mbar_wait(&p_full[t], j & 1);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t vbase = smem_u32(skvb + stage * KV_STAGE_BYTES + K_TILE_BYTES);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {  // 4 x 16 keys; P_t(j) lives in the first 32 columns of S[t][j & 1]
+                const uint64_t bdesc = sdesc_advance_k(make_sdesc_sw128(vbase), ks * 16);
+                mma_ts(tmem_base + TM_O + t * 128, tmem_base + TM_S + t * 128 + (j & 1) * 64 + ks * 8, bdesc, idesc_pv,
+                       (j > 0 || ks > 0) ? 1u : 0u);
+              }
+              if (t == nt - 1) mma_commit(&kv_empty[stage]);  // K_j / V_j fully consumed
+              // the tensor pipe executes in issue order: S_t(j+2) cannot overwrite P_t(j) before P_t(j) V_j is done
+              mma_commit(&o_done[t]);  // P_t(j) V_j retired (phase j): gates O_t rescaling and the epilogue
+              if (j + 2 < nkv) issue_qk(t, j + 2);
+            }
+            __syncwarp();
+          }
+        }
       }
     }
-    }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int t = (warp - 4) / 4;
+    const int quarter = warp % 4;
+    const int row = quarter * 32 + lane;
+    const int r = r0 + t * QT + row;
+    const long off = ((long)s * p.st.Lp + r) * LG_DIM + h * LG_HDIM;
     if (nkv > 0) {
-      // ------------------------------------------------------------------ softmax warpgroups
-      const int t = (warp - 4) / 4;
       if (t < nt) {
-        const int quarter = warp % 4;
-        const int row = quarter * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-        const uint32_t ts = tmem_base + lane_off + TM_S + t * 128;
+        const uint32_t ts0 = tmem_base + lane_off + TM_S + t * 128;
         const uint32_t to = tmem_base + lane_off + TM_O + t * 128;
         float m_used = -INFINITY;
-        uint32_t sv[4][32];  // the whole 128-column S row of this thread: TMEM is read exactly once per block
+        uint32_t sv[2][32];  // the whole 64-column S row of this thread: TMEM is read once per block
         for (int j = 0; j < nkv; ++j) {
-          mbar_wait(&s_full[t], j & 1);
+          const uint32_t ts = ts0 + (j & 1) * 64;
+          mbar_wait(&s_full[2 * t + (j & 1)], (j >> 1) & 1);
           tc_fence_after();
           const int valid = len_kv - j * KB;  // columns >= valid are padding (last block only)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_ld32(ts + c * 32, sv[c]);
+          tmem_ld32(ts, sv[0]);
+          tmem_ld32(ts + 32, sv[1]);
           tmem_ld_wait();
           if (valid < KB) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
               for (int i = 0; i < 32; ++i)
                 if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;  // -inf
           }
           float mx0 = -INFINITY, mx1 = -INFINITY;  // two chains for ILP
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               mx0 = max3(mx0, __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
@@ -225,7 +230,10 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
             if (m_used == -INFINITY) { m_used = mx; }
             else if ((mx - m_used) * SCALE_LOG2 > 8.f) { alpha = ex2((m_used - mx) * SCALE_LOG2); m_used = mx; need = true; }
           }
-          if (__any_sync(0xffffffffu, need)) {  // P_t V of block j-1 has completed (it precedes S_t(j) in issue order)
+          if (__any_sync(0xffffffffu, need)) {
+            // O_t may still be receiving P_t(j-1) V_{j-1} (S_t(j) was issued before it): wait for its commit
+            mbar_wait(&o_done[t], (j - 1) & 1);
+            tc_fence_after();
             uint32_t o32[32];
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -242,10 +250,10 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
             for (int i = 0; i < 16; ++i) o16[i] = __float_as_uint(__uint_as_float(o16[i]) * alpha);
             tmem_st16(to + 64, o16);
           }
-          // P = exp2(c s - c m) as fp16, written over the first 64 columns of S_t
+          // P = exp2(c s - c m) as fp16, written over the first 32 columns of S[t][j & 1]
           const float mc = m_used * SCALE_LOG2;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -265,15 +273,13 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
           mbar_arrive(&p_full[t]);
         }
         // ---- epilogue: O[:, 0:64] / O[:, 64] -> ctx (heads concatenated h-major, lightglue.py:171)
-        mbar_wait(&o_done[t], 0);
+        mbar_wait(&o_done[t], (nkv - 1) & 1);
         tc_fence_after();
-        const int r = r0 + t * QT + row;
         uint32_t o16[16];
         tmem_ld16(to + 64, o16);
         tmem_ld_wait();
         const float l = __uint_as_float(o16[0]);
         const float inv = l > 0.f ? 1.f / l : 0.f;
-        const long off = ((long)s * p.st.Lp + r) * LG_DIM + h * LG_HDIM;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           tmem_ld32(to + c * 32, sv[c]);
@@ -298,17 +304,12 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
           }
         }
       }
-    } else {
-    // no keys: zeros (lightglue.py:114-115)
-    const int t = (warp - 4) / 4;
-    const int r = r0 + t * QT + (warp % 4) * 32 + lane;
-    if (r < len_q) {
-      const long off = ((long)s * p.st.Lp + r) * LG_DIM + h * LG_HDIM;
+    } else if (r < len_q) {
+      // no keys: zeros (lightglue.py:114-115)
       for (int i = 0; i < 8; ++i) {
         reinterpret_cast<uint4*>(p.ctxh + off)[i] = make_uint4(0, 0, 0, 0);
         if (p.ctxl) reinterpret_cast<uint4*>(p.ctxl + off)[i] = make_uint4(0, 0, 0, 0);
       }
-    }
     }
   }
   tc_fence_before();
