@@ -137,6 +137,11 @@ enum { LG_K_ATTENTION = 0, LG_K_LINEAR = 1, LG_K_ASSIGN = 2, LG_K_OTHER = 3, LG_
 LG_API int lg_timing_enable(LgHandle* h, int32_t enable);
 LG_API int lg_kernel_time_ms(LgHandle* h, int32_t kernel_class, double* ms, int64_t* launches);
 
+/* Debug aid: 0, or a code identifying the first in-kernel pipeline wait that timed out since the last
+ * call (the kernels give up instead of hanging); `words32` (optional, 32 entries) receives the
+ * per-site codes.  Synchronises the device. */
+LG_API uint32_t lg_debug_timeout_code(LgHandle* h, uint32_t* words32);
+
 LG_API const char* lg_last_error(void);
 LG_API const char* lg_build_info(void);
 

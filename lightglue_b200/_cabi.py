@@ -13,6 +13,7 @@ ABI_VERSION = 1
 EXPORTS = (
     "lg_weight_blob_floats", "lg_create", "lg_destroy", "lg_workspace_bytes", "lg_forward", "lg_assign",
     "lg_last_launch_count", "lg_timing_enable", "lg_kernel_time_ms", "lg_last_error", "lg_build_info",
+    "lg_debug_timeout_code",
 )
 
 
@@ -82,6 +83,8 @@ def load():
     lib.lg_kernel_time_ms.restype = C.c_int
     lib.lg_kernel_time_ms.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.lg_last_error.restype = C.c_char_p
+    lib.lg_debug_timeout_code.restype = C.c_uint32
+    lib.lg_debug_timeout_code.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     lib.lg_build_info.restype = C.c_char_p
     _lib = lib
     return lib

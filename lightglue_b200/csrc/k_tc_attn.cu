@@ -45,6 +45,7 @@ struct AttnParams {
   __nv_bfloat16* ctxh; __nv_bfloat16* ctxl;
   int kv_shift;
   SeqState st;
+  unsigned int* dbg;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -91,9 +92,13 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + KV_STAGES;
   uint64_t* s_full = kv_empty + KV_STAGES;   // [t][b] -> s_full[2 * t + b]
-  uint64_t* p_full = s_full + 4;             // [2]
-  uint64_t* o_done = p_full + 2;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* p_full = s_full + 4;             // [t][b]: the softmax may run one block ahead of the MMA warp,
+                                             // so P(j) and P(j+1) need separate barriers (no phase lapping)
+  uint64_t* o_done = p_full + 4;             // [2] one phase per block (only ever tested for block j-1 during block j)
+  uint64_t* o_final = o_done + 2;            // [2] single phase: last P V of the tile retired.  (The softmax
+                                             // runs ahead of the MMA warp, so a parity test on o_done for the
+                                             // last block could alias an older phase.)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
@@ -111,8 +116,8 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
     tma_prefetch_desc(&p.vt_map);
     mbar_init(q_full, 1);
     for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
-    for (int t = 0; t < 2; ++t) { mbar_init(&p_full[t], 128); mbar_init(&o_done[t], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); }
+    for (int t = 0; t < 2; ++t) { mbar_init(&o_done[t], 1); mbar_init(&o_final[t], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
           tma_load_3d(sq + Q_TILE_BYTES, &p.q_map, 0, r0 + QT, s * LG_HEADS + h, q_full);
           for (int j = 0; j < nkv; ++j) {
             const int stage = j % KV_STAGES, round = j / KV_STAGES;
-            mbar_wait(&kv_empty[stage], (round & 1) ^ 1);
+            mbar_wait(&kv_empty[stage], (round & 1) ^ 1, p.dbg, 1, j);
             uint8_t* dst = skvb + stage * KV_STAGE_BYTES;
             mbar_arrive_expect_tx(&kv_full[stage], K_TILE_BYTES + V_TMA_BYTES);
             tma_load_3d(dst, &p.k_map, 0, j * KB, skv * LG_HEADS + h, &kv_full[stage]);
@@ -152,9 +157,9 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
                    idesc_qk, k > 0 ? 1u : 0u);
           mma_commit(&s_full[2 * t + (j & 1)]);
         };
-        mbar_wait(q_full, 0);
+        mbar_wait(q_full, 0, p.dbg, 2);
         for (int j = 0; j < 2 && j < nkv; ++j) {  // prologue: S_t(0), S_t(1)
-          mbar_wait(&kv_full[j % KV_STAGES], 0);
+          mbar_wait(&kv_full[j % KV_STAGES], 0, p.dbg, 3);
           tc_fence_after();
           if (lane == 0)
             for (int t = 0; t < nt; ++t) issue_qk(t, j);
@@ -162,9 +167,9 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
         }
         for (int j = 0; j < nkv; ++j) {
           const int stage = j % KV_STAGES;
-          if (j + 2 < nkv) mbar_wait(&kv_full[(j + 2) % KV_STAGES], ((j + 2) / KV_STAGES) & 1);
+          if (j + 2 < nkv) mbar_wait(&kv_full[(j + 2) % KV_STAGES], ((j + 2) / KV_STAGES) & 1, p.dbg, 4, j);
           for (int t = 0; t < nt; ++t) {
-            mbar_wait(&p_full[t], j & 1);
+            mbar_wait(&p_full[2 * t + (j & 1)], (j >> 1) & 1, p.dbg, 5, j * 2 + t);
             tc_fence_after();
             if (lane == 0) {
               const uint32_t vbase = smem_u32(skvb + stage * KV_STAGE_BYTES + K_TILE_BYTES);
@@ -176,8 +181,9 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
               }
               if (t == nt - 1) mma_commit(&kv_empty[stage]);  // K_j / V_j fully consumed
               // the tensor pipe executes in issue order: S_t(j+2) cannot overwrite P_t(j) before P_t(j) V_j is done
-              mma_commit(&o_done[t]);  // P_t(j) V_j retired (phase j): gates O_t rescaling and the epilogue
+              mma_commit(&o_done[t]);  // P_t(j) V_j retired (phase j): gates the lazy rescaling of O_t
               if (j + 2 < nkv) issue_qk(t, j + 2);
+              else if (j + 1 == nkv) mma_commit(&o_final[t]);  // single-phase: everything for tile t has retired
             }
             __syncwarp();
           }
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
         uint32_t sv[2][32];  // the whole 64-column S row of this thread: TMEM is read once per block
         for (int j = 0; j < nkv; ++j) {
           const uint32_t ts = ts0 + (j & 1) * 64;
-          mbar_wait(&s_full[2 * t + (j & 1)], (j >> 1) & 1);
+          mbar_wait(&s_full[2 * t + (j & 1)], (j >> 1) & 1, p.dbg, 6, j * 2 + t);
           tc_fence_after();
           const int valid = len_kv - j * KB;  // columns >= valid are padding (last block only)
           tmem_ld32(ts, sv[0]);
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
           }
           if (__any_sync(0xffffffffu, need)) {
             // O_t may still be receiving P_t(j-1) V_{j-1} (S_t(j) was issued before it): wait for its commit
-            mbar_wait(&o_done[t], (j - 1) & 1);
+            mbar_wait(&o_done[t], (j - 1) & 1, p.dbg, 7, j * 2 + t);
             tc_fence_after();
             uint32_t o32[32];
 #pragma unroll
@@ -270,10 +276,10 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
           }
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&p_full[t]);
+          mbar_arrive(&p_full[2 * t + (j & 1)]);
         }
         // ---- epilogue: O[:, 0:64] / O[:, 64] -> ctx (heads concatenated h-major, lightglue.py:171)
-        mbar_wait(&o_done[t], (nkv - 1) & 1);
+        mbar_wait(&o_final[t], 0, p.dbg, 8, t);
         tc_fence_after();
         uint32_t o16[16];
         tmem_ld16(to + 64, o16);
@@ -472,7 +478,7 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
   }
   AttnParams p;
   p.q_map = c->qm; p.k_map = c->km; p.vt_map = c->vm;
-  p.ctxh = b.ctxh; p.ctxl = b.ctxl; p.kv_shift = kv_shift; p.st = st;
+  p.ctxh = b.ctxh; p.ctxl = b.ctxl; p.kv_shift = kv_shift; p.st = st; p.dbg = h->tc.dbg;
   constexpr int smem = 2 * Q_TILE_BYTES + KV_STAGES * KV_STAGE_BYTES + 1024 + 256;
   static bool attr = false;
   if (!attr) {

@@ -41,6 +41,7 @@ struct TcLinParams {
   __nv_bfloat16* out_h; __nv_bfloat16* out_l; int ldb;
   __half* q; __half* k; __half* vt; const float* cs;
   const float* ln_g; const float* ln_b;
+  unsigned int* dbg;
 };
 
 __device__ __forceinline__ void split_store(__nv_bfloat16* hi, __nv_bfloat16* lo, const float (&v)[32]) {
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(192, NSLOT == 1 ? 2 : 1) tc_linear_kernel(cons
     if (lane == 0) {
       for (int it = 0; it < iters; ++it) {
         const int stage = it % STAGES, round = it / STAGES;
-        mbar_wait(&empty[stage], (round & 1) ^ 1);
+        mbar_wait(&empty[stage], (round & 1) ^ 1, p.dbg, 17);
         const int pass = it / p.kb_total, kb = it % p.kb_total;
         // pass order (x3): A_lo*W_hi, A_hi*W_lo, A_hi*W_hi ; (bf16): A_hi*W_hi
         const bool a_lo = (p.passes == 3) && pass == 0;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(192, NSLOT == 1 ? 2 : 1) tc_linear_kernel(cons
     constexpr uint32_t idesc = make_idesc(BM, BN, true);
     for (int it = 0; it < iters; ++it) {
       const int stage = it % STAGES, round = it / STAGES;
-      mbar_wait(&full[stage], round & 1);
+      mbar_wait(&full[stage], round & 1, p.dbg, 18);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(192, NSLOT == 1 ? 2 : 1) tc_linear_kernel(cons
     const long grow = grow0 + row;
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float* bias = p.bias + (p.w_select ? (long)sel * p.bias_sel_stride : 0);
-    mbar_wait(acc_full, 0);
+    mbar_wait(acc_full, 0, p.dbg, 19);
     tc_fence_after();
     uint32_t raw[32];
     float v[32];
@@ -422,6 +423,7 @@ int run_linear(LgHandle* h, const SeqState& st, const LinDesc& d, TcLinParams& p
   p.passes = x3 ? 3 : 1;
   p.st = st;
   p.w_select = d.nsel > 1;
+  p.dbg = h->tc.dbg;
   h->launches += 1;
   if (p.epi == TEPI_LN_GELU) return launch_linear<2, 2>(p, 1, stream);
   return launch_linear<1, 2>(p, d.nout / BN, stream);
@@ -431,6 +433,19 @@ int run_linear(LgHandle* h, const SeqState& st, const LinDesc& d, TcLinParams& p
 // ------------------------------------------------------------------------------------------------
 // entry points used by lg_api.cu
 // ------------------------------------------------------------------------------------------------
+unsigned int tc_debug_timeout_code(LgHandle* h, unsigned int* words32) {
+  unsigned int v[32] = {0};
+  if (!h->tc.dbg) return 0;
+  if (cudaMemcpy(v, h->tc.dbg, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 0xffffffffu;
+  unsigned int first = 0;
+  for (int i = 0; i < 32; ++i) {
+    if (words32) words32[i] = v[i];
+    if (v[i] && !first) first = (unsigned)i << 24 | (v[i] & 0x80ffffffu);
+  }
+  if (first) cudaMemset(h->tc.dbg, 0, sizeof(v));
+  return first;
+}
+
 int tc_pack_weights(LgHandle* h, cudaStream_t stream) {
   TcWeights& w = h->tc;
   const size_t n = h->wpk_floats;
@@ -441,6 +456,9 @@ int tc_pack_weights(LgHandle* h, cudaStream_t stream) {
   split_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(h->wpk, w.w_hi, w.w_lo, n);
   LG_CHECK_LAUNCH();
   w.map_cache = new MapCache();
+  e = cudaMalloc(&w.dbg, 32 * sizeof(unsigned int));
+  if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
+  cudaMemsetAsync(w.dbg, 0, 32 * sizeof(unsigned int), stream);
   if (!get_encode()) return lg_set_error("cuTensorMapEncodeTiled unavailable (driver too old?)");
   return 0;
 }
@@ -449,6 +467,8 @@ void tc_free_weights(TcWeights* w) {
   if (w->w_hi) cudaFree(w->w_hi);
   if (w->w_lo) cudaFree(w->w_lo);
   if (w->map_cache) delete static_cast<MapCache*>(w->map_cache);
+  if (w->dbg) cudaFree(w->dbg);
+  w->dbg = nullptr;
   w->w_hi = w->w_lo = nullptr;
   w->map_cache = nullptr;
 }

@@ -178,6 +178,8 @@ extern "C" int lg_destroy(LgHandle* h) {
   return 0;
 }
 
+extern "C" uint32_t lg_debug_timeout_code(LgHandle* h, uint32_t* words32) { return h ? tc_debug_timeout_code(h, words32) : 0; }
+
 extern "C" int64_t lg_last_launch_count(const LgHandle* h) { return h ? h->launches : 0; }
 
 extern "C" int lg_timing_enable(LgHandle* h, int32_t enable) {

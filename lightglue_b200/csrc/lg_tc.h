@@ -14,6 +14,7 @@ struct TcWeights {
   __nv_bfloat16* w_hi;
   __nv_bfloat16* w_lo;
   void* map_cache;  // CUtensorMap cache keyed by (pointer, shape)
+  unsigned int* dbg;  // device word: site code of the first pipeline wait that timed out (0 = none)
 };
 // per-forward activation buffers carved from the workspace (lo = null in LG_PREC_BF16)
 struct TcBuffers {
@@ -37,3 +38,5 @@ int tc_final_proj(LgHandle* h, const TcBuffers& b, const SeqState& st, float* p_
 // softmax(q k^T / 8) v per (sequence, head): q from b.q, keys from kbuf, values from b.vt; key/value
 // sequence = (s + kv_shift) % S; writes b.ctxh (/ b.ctxl)
 int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shift, const __half* kbuf, cudaStream_t stream);
+// 0, or the site code of the first mbarrier wait that timed out since the last call (synchronises)
+unsigned int tc_debug_timeout_code(LgHandle* h, unsigned int* words32);

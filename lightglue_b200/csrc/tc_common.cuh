@@ -35,11 +35,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug traps (visible as a launch failure) instead of hanging the GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded spin: a protocol bug must never hang the GPU box.  After ~2^20 failed probes the waiter records
+// a site code in g_tc_timeout (read back by lg_debug_timeout_code()) and gives up; the kernel then
+// finishes with garbage instead of dead-locking, and the host can report where it stalled.
+// dbg points at 32 words; word `site` keeps the first code recorded there: 0x80000000 | extra << 12 | thread.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, uint32_t site,
+                                          uint32_t extra = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 18)) {
+      if (dbg) atomicCAS(dbg + (site & 31), 0u, 0x80000000u | ((extra & 0xffff) << 12) | (threadIdx.x & 0xfff));
+      return;
+    }
   }
 }
 

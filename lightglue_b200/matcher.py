@@ -380,5 +380,14 @@ class LightGlue(nn.Module):
         lib.lg_timing_enable(self._handle[0], 0)
         return res
 
+    def debug_timeout_code(self) -> int:
+        """0, or the site code of an in-kernel pipeline wait that timed out (debug aid; synchronises)."""
+        if self._handle is None:
+            return 0
+        words = (C.c_uint32 * 32)()
+        code = int(_cabi.load().lg_debug_timeout_code(self._handle[0], words))
+        self.debug_words = [int(w) for w in words]
+        return code
+
     def last_launch_count(self) -> int:
         return 0 if self._handle is None else int(_cabi.load().lg_last_launch_count(self._handle[0]))
