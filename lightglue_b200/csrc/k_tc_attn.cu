@@ -15,7 +15,8 @@
 // result is directly the packed fp16 P operand.
 // TMEM map (512 columns): S[t][b] at 128*t + 64*b (P aliases its first 32 columns) | O0 256-335 | O1 384-463.
 // Warp roles (384 threads = 3 warpgroups): warpgroup 0 = {warp 0 TMA producer, warp 1 TMEM owner + MMA
-// issuer, 2 idle warps} shrinks its registers (setmaxnreg.dec); warpgroups 1 and 2 are the softmax
+// issuer of tile 0, warp 2 MMA issuer of tile 1, 1 idle warp} shrinks its registers (setmaxnreg.dec);
+// warpgroups 1 and 2 are the softmax
 // warpgroups of query tile 0 / 1 (one query row per thread; warp w reads TMEM lanes 32*(w%4)..).
 #include <stdlib.h>
 
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
     tma_prefetch_desc(&p.k_map);
     tma_prefetch_desc(&p.vt_map);
     mbar_init(q_full, 1);
-    for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], nt); }
     for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); }
     for (int t = 0; t < 2; ++t) { mbar_init(&o_done[t], 1); mbar_init(&o_final[t], 1); }
     fence_barrier_init();
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
     if (nkv > 0) {
       if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
           mbar_arrive_expect_tx(q_full, 2 * Q_TILE_BYTES);
           tma_load_3d(sq, &p.q_map, 0, r0, s * LG_HEADS + h, q_full);
           tma_load_3d(sq + Q_TILE_BYTES, &p.q_map, 0, r0 + QT, s * LG_HEADS + h, q_full);
@@ -144,49 +145,50 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
             tma_load_3d(dst + K_TILE_BYTES, &p.vt_map, j * KB, 0, skv * LG_HEADS + h, &kv_full[stage]);
           }
         }
-      } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
+      } else if (warp - 1 < nt) {
+        // ------------------------------------------------------------------ MMA issuers: warp 1 -> tile 0, warp 2 -> tile 1
+        // (one issuing warp per query tile: the single-thread issue path -- descriptor moves to uniform
+        //  registers, tcgen05.mma, tcgen05.commit -- is long enough to bound the kernel if one warp serves both)
+        const int t = warp - 1;
         constexpr uint32_t idesc_qk = make_idesc(QT, KB, false);      // M=128 N=64, fp16
         constexpr uint32_t idesc_pv = make_idesc(QT, V_ROWS, false);  // M=128 N=80, fp16
-        auto issue_qk = [&](int t, int j) {  // S[t][j & 1] = Q_t K_j^T
-          const uint64_t adesc = make_sdesc_sw128(smem_u32(sq + t * Q_TILE_BYTES));
-          const uint64_t bdesc = make_sdesc_sw128(smem_u32(skvb + (j % KV_STAGES) * KV_STAGE_BYTES));
+        const uint64_t qdesc = make_sdesc_sw128(smem_u32(sq + t * Q_TILE_BYTES));
+        const uint64_t kdesc0 = make_sdesc_sw128(smem_u32(skvb));
+        const uint64_t vdesc0 = make_sdesc_sw128(smem_u32(skvb + K_TILE_BYTES));
+        const uint32_t ts_addr = tmem_base + TM_S + t * 128;
+        const uint32_t to_addr = tmem_base + TM_O + t * 128;
+        auto issue_qk = [&](int j) {  // S[t][j & 1] = Q_t K_j^T   (called by one elected lane)
+          const uint64_t kdesc = kdesc0 + (uint64_t)((j % KV_STAGES) * (KV_STAGE_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            mma_ss(tmem_base + TM_S + t * 128 + (j & 1) * 64, sdesc_advance_k(adesc, k * 16), sdesc_advance_k(bdesc, k * 16),
-                   idesc_qk, k > 0 ? 1u : 0u);
+            mma_ss(ts_addr + (j & 1) * 64, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
           mma_commit(&s_full[2 * t + (j & 1)]);
         };
         mbar_wait(q_full, 0, p.dbg, 2);
         for (int j = 0; j < 2 && j < nkv; ++j) {  // prologue: S_t(0), S_t(1)
           mbar_wait(&kv_full[j % KV_STAGES], 0, p.dbg, 3);
           tc_fence_after();
-          if (lane == 0)
-            for (int t = 0; t < nt; ++t) issue_qk(t, j);
+          if (elect_one()) issue_qk(j);
           __syncwarp();
         }
         for (int j = 0; j < nkv; ++j) {
           const int stage = j % KV_STAGES;
           if (j + 2 < nkv) mbar_wait(&kv_full[(j + 2) % KV_STAGES], ((j + 2) / KV_STAGES) & 1, p.dbg, 4, j);
-          for (int t = 0; t < nt; ++t) {
-            mbar_wait(&p_full[2 * t + (j & 1)], (j >> 1) & 1, p.dbg, 5, j * 2 + t);
-            tc_fence_after();
-            if (lane == 0) {
-              const uint32_t vbase = smem_u32(skvb + stage * KV_STAGE_BYTES + K_TILE_BYTES);
+          mbar_wait(&p_full[2 * t + (j & 1)], (j >> 1) & 1, p.dbg, 5, j * 2 + t);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t vdesc = vdesc0 + (uint64_t)(stage * (KV_STAGE_BYTES >> 4));
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {  // 4 x 16 keys; P_t(j) lives in the first 32 columns of S[t][j & 1]
-                const uint64_t bdesc = sdesc_advance_k(make_sdesc_sw128(vbase), ks * 16);
-                mma_ts(tmem_base + TM_O + t * 128, tmem_base + TM_S + t * 128 + (j & 1) * 64 + ks * 8, bdesc, idesc_pv,
-                       (j > 0 || ks > 0) ? 1u : 0u);
-              }
-              if (t == nt - 1) mma_commit(&kv_empty[stage]);  // K_j / V_j fully consumed
-              // the tensor pipe executes in issue order: S_t(j+2) cannot overwrite P_t(j) before P_t(j) V_j is done
-              mma_commit(&o_done[t]);  // P_t(j) V_j retired (phase j): gates the lazy rescaling of O_t
-              if (j + 2 < nkv) issue_qk(t, j + 2);
-              else if (j + 1 == nkv) mma_commit(&o_final[t]);  // single-phase: everything for tile t has retired
-            }
-            __syncwarp();
+            for (int ks = 0; ks < 4; ++ks)  // 4 x 16 keys; P_t(j) lives in the first 32 columns of S[t][j & 1]
+              mma_ts(to_addr, ts_addr + (j & 1) * 64 + ks * 8, vdesc + 2 * ks, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+            mma_commit(&kv_empty[stage]);  // this tile is done with K_j / V_j (the barrier expects nt arrivals)
+            mma_commit(&o_done[t]);        // P_t(j) V_j retired (phase j): gates the lazy rescaling of O_t
+            // the tensor pipe executes one thread's MMAs in issue order: S_t(j+2) cannot overwrite P_t(j)
+            // before P_t(j) V_j has read it
+            if (j + 2 < nkv) issue_qk(j + 2);
+            else if (j + 1 == nkv) mma_commit(&o_final[t]);  // single phase: everything for tile t has retired
           }
+          __syncwarp();
         }
       }
     }

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(192, NSLOT == 1 ? 2 : 1) tc_linear_kernel(cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {  // (elect.sync lets ptxas issue the TMA / MMA instructions without a per-lane loop)
       for (int it = 0; it < iters; ++it) {
         const int stage = it % STAGES, round = it / STAGES;
         mbar_wait(&empty[stage], (round & 1) ^ 1, p.dbg, 17);
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(192, NSLOT == 1 ? 2 : 1) tc_linear_kernel(cons
       const int stage = it % STAGES, round = it / STAGES;
       mbar_wait(&full[stage], round & 1, p.dbg, 18);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
         const uint64_t adesc = make_sdesc_sw128(sa);
 #pragma unroll
