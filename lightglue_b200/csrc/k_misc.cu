@@ -591,6 +591,23 @@ __global__ void __launch_bounds__(1024) assign_output_kernel(AssignArgs a, SeqSt
   if (tid == 0) a.n_matches[b] = carry;
 }
 
+int misc_assign_z(const AssignArgs& a, const SeqState& st, cudaStream_t stream) {
+  assign_z_kernel<<<dim3(st.Lp / 8, st.S), 256, 0, stream>>>(a, st);
+  LG_CHECK_LAUNCH();
+  return 0;
+}
+
+// mutual-nearest filter + output assembly on row/column arg-max results already in slot 0 of
+// rowbest/rowarg/colbest/colarg (used after the tensor-core sweeps)
+int misc_assign_tail(const AssignArgs& a, const SeqState& st, cudaStream_t stream, int64_t* launches) {
+  assign_filter_kernel<<<dim3((st.Lp + 255) / 256, st.B), 256, 0, stream>>>(a, st);
+  LG_CHECK_LAUNCH();
+  assign_output_kernel<<<st.B, 1024, 0, stream>>>(a, st);
+  LG_CHECK_LAUNCH();
+  *launches += 2;
+  return 0;
+}
+
 int misc_assign(const AssignArgs& a, const SeqState& st, cudaStream_t stream, int64_t* launches) {
   const int B = st.B;
   const int tiles = st.Lp / 64;

@@ -26,7 +26,7 @@ constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int W_TILE_BYTES = BN * BK * 2;  // 32 KB
 
-enum { TEPI_QKV = 0, TEPI_BF16 = 1, TEPI_LN_GELU = 2, TEPI_RESID = 3, TEPI_F32 = 4 };
+enum { TEPI_QKV = 0, TEPI_BF16 = 1, TEPI_LN_GELU = 2, TEPI_RESID = 3, TEPI_F32 = 4, TEPI_LSE = 5, TEPI_ARGMAX = 6 };
 
 struct TcLinParams {
   CUtensorMap a_hi[2], a_lo[2];  // A segment 0 / 1
@@ -35,6 +35,9 @@ struct TcLinParams {
   int epi, rope;
   SeqState st;
   int w_select;                  // 1: third TMA coordinate / bias offset = stop_layer[pair] - 1
+                                 // 2: third TMA coordinate = partner sequence (similarity sweeps of the assignment)
+  float* part; int* part_arg; int part_stride;  // TEPI_LSE: (max, sumexp) pairs; TEPI_ARGMAX: best / arg, [S*Lp, part_stride]
+  const float* term;             // TEPI_ARGMAX: logsigmoid(z) - LSE per token, [S, Lp]
   const float* bias; long bias_sel_stride;
   float scale;
   float* out_f32; int ldo;
@@ -63,6 +66,8 @@ __device__ __forceinline__ void split_store(__nv_bfloat16* hi, __nv_bfloat16* lo
   }
 }
 
+__device__ __forceinline__ int n_tile_of(int bx) { return bx; }
+
 template <int NSLOT, int STAGES>
 __global__ void __launch_bounds__(192, NSLOT == 1 ? 2 : 1) tc_linear_kernel(const __grid_constant__ TcLinParams p) {
   constexpr int STAGE_BYTES = A_TILE_BYTES + NSLOT * W_TILE_BYTES;
@@ -75,8 +80,10 @@ __global__ void __launch_bounds__(192, NSLOT == 1 ? 2 : 1) tc_linear_kernel(cons
   const int pair = s >= p.st.B ? s - p.st.B : s;
   const int sl = p.st.stop_layer[pair];
   int sel = 0;
-  if (p.w_select) sel = sl - 1;
+  if (p.w_select == 1) sel = sl - 1;
+  else if (p.w_select == 2) sel = s >= p.st.B ? s - p.st.B : s + p.st.B;
   else if (sl != 0) return;  // pair already exited (lightglue.py:549-550)
+  if (p.w_select == 2 && n_tile_of(blockIdx.x) * BN >= p.st.len[sel]) return;  // no live columns in this tile
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -153,12 +160,60 @@ __global__ void __launch_bounds__(192, NSLOT == 1 ? 2 : 1) tc_linear_kernel(cons
     const bool live = r < len;                    // padding rows are never written
     const long grow = grow0 + row;
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const float* bias = p.bias + (p.w_select ? (long)sel * p.bias_sel_stride : 0);
+    const float* bias = p.bias + (p.w_select == 1 ? (long)sel * p.bias_sel_stride : 0);
     mbar_wait(acc_full, 0, p.dbg, 19);
     tc_fence_after();
     uint32_t raw[32];
     float v[32];
-    if (p.epi == TEPI_LN_GELU) {
+    if (p.epi == TEPI_LSE || p.epi == TEPI_ARGMAX) {
+      // Assignment sweeps (lightglue.py:265-277, 302-305) on a 128 x 256 tile of S = p_s p_partner^T.  One row
+      // per thread, so every row reduction is thread-local; the transposed problem (partner as rows) is a
+      // second launch row, which makes the column reductions of the reference row reductions too.
+      const int ncols = p.st.len[sel] - n_tile * BN;  // live columns of this tile (> 0)
+      if (p.epi == TEPI_LSE) {
+        float m = -INFINITY, se = 0.f;  // online (max, sum-exp) over the tile's live columns
+        for (int c0 = 0; c0 < BN && c0 < ncols; c0 += 32) {
+          tmem_ld32(tlane + c0, raw);
+          tmem_ld_wait();
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = (c0 + j < ncols) ? __uint_as_float(raw[j]) : -INFINITY;
+            cm = fmaxf(cm, v[j]);
+          }
+          if (cm > m) { se *= expf(m - cm); m = cm; }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) se += expf(v[j] - m);
+        }
+        if (live) {
+          float2* o = reinterpret_cast<float2*>(p.part) + grow * p.part_stride + n_tile;
+          *o = make_float2(m, se);
+        }
+      } else {
+        // score = 2 S + term_s[i] + term_partner[j]; the row term is constant per thread and does not move the arg-max
+        const float* ct = p.term + (long)sel * p.st.Lp + n_tile * BN;
+        float best = -INFINITY; int arg = 0;
+        for (int c0 = 0; c0 < BN && c0 < ncols; c0 += 32) {
+          tmem_ld32(tlane + c0, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(ct + c0) + j4);
+            const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = j4 * 4 + jj;
+              const float sc = fmaf(2.f, __uint_as_float(raw[j]), cc[jj]);
+              if (c0 + j < ncols && sc > best) { best = sc; arg = n_tile * BN + c0 + j; }  // first max wins ties
+            }
+          }
+        }
+        if (live) {
+          p.part[grow * p.part_stride + n_tile] = best + p.term[grow];
+          p.part_arg[grow * p.part_stride + n_tile] = arg;
+        }
+      }
+    } else if (p.epi == TEPI_LN_GELU) {
       // LayerNorm(512, eps 1e-5) + exact GELU (lightglue.py:154-155): three sweeps over the TMEM row
       float sum = 0.f;
       for (int c0 = 0; c0 < NSLOT * BN; c0 += 32) {
@@ -422,7 +477,7 @@ int run_linear(LgHandle* h, const SeqState& st, const LinDesc& d, TcLinParams& p
   p.kb_total = K / BK;
   p.passes = x3 ? 3 : 1;
   p.st = st;
-  p.w_select = d.nsel > 1;
+  if (p.w_select != 2) p.w_select = d.nsel > 1;
   p.dbg = h->tc.dbg;
   h->launches += 1;
   if (p.epi == TEPI_LN_GELU) return launch_linear<2, 2>(p, 1, stream);
@@ -433,6 +488,79 @@ int run_linear(LgHandle* h, const SeqState& st, const LinDesc& d, TcLinParams& p
 // ------------------------------------------------------------------------------------------------
 // entry points used by lg_api.cu
 // ------------------------------------------------------------------------------------------------
+
+// ------------------------------------------------------------------------------------------------
+// Assignment tail on the tensor cores (matches-only variant: the log-assignment matrix is never written)
+// ------------------------------------------------------------------------------------------------
+namespace {
+// partial (max, sumexp) per 256-column tile -> term[s][r] = logsigmoid(z) - LSE  (lightglue.py:270-274)
+__global__ void assign_lse_combine_kernel(const float* __restrict__ part, const float* __restrict__ z, float* __restrict__ term,
+                                          int ntc, SeqState st) {
+  const int s = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= st.len[s]) return;
+  const int partner = s >= st.B ? s - st.B : s + st.B;
+  const int nt = (st.len[partner] + BN - 1) / BN;
+  const float2* pt = reinterpret_cast<const float2*>(part) + ((long)s * st.Lp + r) * ntc;
+  float m = -INFINITY;
+  for (int t = 0; t < nt; ++t) m = fmaxf(m, pt[t].x);
+  float se = 0.f;
+  for (int t = 0; t < nt; ++t) se += pt[t].y * expf(pt[t].x - m);
+  const float zz = z[(long)s * st.Lp + r];
+  term[(long)s * st.Lp + r] = fminf(zz, 0.f) - log1pf(expf(-fabsf(zz))) - (m + logf(se));
+}
+// per-tile (best, arg) -> slot 0 of the [B, Lp, nt64] arrays the mutual-nearest filter reads
+__global__ void assign_best_combine_kernel(const float* __restrict__ part, const int* __restrict__ part_arg, int ntc,
+                                           float* rowbest, int* rowarg, float* colbest, int* colarg, int nt64, SeqState st) {
+  const int s = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= st.len[s]) return;
+  const int partner = s >= st.B ? s - st.B : s + st.B;
+  const int nt = (st.len[partner] + BN - 1) / BN;
+  const long base = ((long)s * st.Lp + r) * ntc;
+  float best = -INFINITY; int arg = 0;
+  for (int t = 0; t < nt; ++t)
+    if (part[base + t] > best) { best = part[base + t]; arg = part_arg[base + t]; }
+  const int b = s >= st.B ? s - st.B : s;
+  const long o = ((long)b * st.Lp + r) * nt64;
+  if (s < st.B) { rowbest[o] = best; rowarg[o] = arg; }
+  else { colbest[o] = best; colarg[o] = arg; }
+}
+}  // namespace
+
+int tc_assign_sweeps(LgHandle* h, const TcBuffers& b, const SeqState& st, const float* z, float* part, int* part_arg,
+                     float* term, float* rowbest, int* rowarg, float* colbest, int* colarg, int nt64, cudaStream_t stream) {
+  const int ntc = (st.Lp + BN - 1) / BN;
+  for (int sweep = 0; sweep < 2; ++sweep) {
+    TcLinParams p{};
+    p.epi = sweep == 0 ? TEPI_LSE : TEPI_ARGMAX;
+    p.scale = 1.f; p.bias = h->wpk;  // unused
+    p.part = part; p.part_arg = part_arg; p.part_stride = ntc; p.term = term;
+    p.w_select = 2;
+    const bool x3 = h->cfg.precision == LG_PREC_BF16X3;
+    const uint64_t rows = (uint64_t)st.S * st.Lp;
+    int r;
+    if ((r = amap(h, &p.a_hi[0], b.msgh, rows, LG_DIM))) return r;
+    p.a_hi[1] = p.a_hi[0]; p.a_lo[0] = p.a_hi[0]; p.a_lo[1] = p.a_hi[0];
+    if (x3) { if ((r = amap(h, &p.a_lo[0], b.msgl, rows, LG_DIM))) return r; p.a_lo[1] = p.a_lo[0]; }
+    if ((r = wmap(h, &p.w_hi, b.msgh, st.Lp, LG_DIM, st.S, (uint64_t)st.Lp * LG_DIM))) return r;
+    p.w_lo = p.w_hi;
+    if (x3 && (r = wmap(h, &p.w_lo, b.msgl, st.Lp, LG_DIM, st.S, (uint64_t)st.Lp * LG_DIM))) return r;
+    p.kb0 = LG_DIM / BK; p.kb_total = LG_DIM / BK; p.passes = x3 ? 3 : 1;
+    p.st = st; p.dbg = h->tc.dbg;
+    h->launches += 1;
+    if ((r = launch_linear<1, 2>(p, ntc, stream))) return r;
+    if (sweep == 0) {
+      assign_lse_combine_kernel<<<dim3((st.Lp + 255) / 256, st.S), 256, 0, stream>>>(part, z, term, ntc, st);
+      LG_CHECK_LAUNCH();
+      h->launches += 1;
+    }
+  }
+  assign_best_combine_kernel<<<dim3((st.Lp + 255) / 256, st.S), 256, 0, stream>>>(part, part_arg, ntc, rowbest, rowarg, colbest,
+                                                                                    colarg, nt64, st);
+  LG_CHECK_LAUNCH();
+  h->launches += 1;
+  return 0;
+}
+
 unsigned int tc_debug_timeout_code(LgHandle* h, unsigned int* words32) {
   unsigned int v[32] = {0};
   if (!h->tc.dbg) return 0;
@@ -518,7 +646,7 @@ int tc_final_proj(LgHandle* h, const TcBuffers& b, const SeqState& st, float* p_
   TcLinParams p{};
   p.epi = TEPI_F32; p.scale = 0.25f;  // / 256^(1/4) (lightglue.py:291)
   p.bias = h->wpk + h->o_assign + AO_FB; p.bias_sel_stride = ASSIGN_BLOB_PAD;
-  p.out_f32 = p_out; p.ldo = LG_DIM; p.out_h = nullptr; p.out_l = nullptr; p.ldb = LG_DIM;
+  p.out_f32 = p_out; p.ldo = LG_DIM; p.out_h = b.msgh; p.out_l = b.msgl; p.ldb = LG_DIM;  // bf16 images feed the sweeps
   LinDesc ld{b.xh, b.xl, LG_DIM, nullptr, nullptr, 0, h->o_assign + AO_FW, LG_DIM, h->cfg.n_layers, ASSIGN_BLOB_PAD};
   return run_linear(h, st, ld, p, stream);
 }

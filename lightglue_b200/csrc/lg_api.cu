@@ -220,7 +220,7 @@ struct Bump {
 
 struct Workspace {
   int Lp, nt;
-  float *xa, *xb, *csa, *csb, *q, *k, *v, *ctx, *msg, *hbuf, *z;
+  float *xa, *xb, *csa, *csb, *q, *k, *v, *ctx, *msg, *hbuf, *z, *term;
   float *rowpart, *colpart, *rowlse, *collse, *rowbest, *colbest, *ms0c, *ms1c;
   int *rowarg, *colarg, *m0c, *m1c;
   int *lena, *lenb, *inda, *indb, *prune, *stop_layer, *below, *pos, *did_prune;
@@ -259,6 +259,7 @@ void carve(const LgHandle* h, int B, int M, int N, char* base, Workspace* w) {
     tc_carve(&b.off, base, S, Lp, h, &w->tc);
   }
   w->z = b.take<float>(R);
+  w->term = b.take<float>(R);
   const size_t P = (size_t)B * Lp;
   w->rowpart = b.take<float>(P * w->nt * 2);
   w->colpart = b.take<float>(P * w->nt * 2);
@@ -333,7 +334,16 @@ static int run_assign(LgHandle* h, const Workspace& w, const SeqState& st, const
   a.log_assignment = out->log_assignment;
   {
     Timer t(h, LG_K_ASSIGN, stream);
-    RC(misc_assign(a, st, stream, &h->launches));
+    if (h->cfg.precision != LG_PREC_FP32 && !out->log_assignment && st.Lp >= 256) {
+      // matches-only variant: both similarity sweeps on the tensor cores, nothing N x M ever reaches HBM
+      RC(misc_assign_z(a, st, stream));
+      h->launches += 1;
+      RC(tc_assign_sweeps(h, w.tc, st, w.z, w.rowpart, reinterpret_cast<int*>(w.colpart), w.term, w.rowbest, w.rowarg,
+                          w.colbest, w.colarg, w.nt, stream));
+      RC(misc_assign_tail(a, st, stream, &h->launches));
+    } else {
+      RC(misc_assign(a, st, stream, &h->launches));
+    }
   }
   return 0;
 }
