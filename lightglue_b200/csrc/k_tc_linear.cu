@@ -31,7 +31,7 @@ enum { TEPI_QKV = 0, TEPI_BF16 = 1, TEPI_LN_GELU = 2, TEPI_RESID = 3, TEPI_F32 =
 struct TcLinParams {
   CUtensorMap a_hi[2], a_lo[2];  // A segment 0 / 1
   CUtensorMap w_hi, w_lo;        // 3-D: (K, Nout, select)
-  int kb0, kb_total, passes;
+  int kb0, kb_total, passes, n_tiles;
   int epi, rope;
   SeqState st;
   int w_select;                  // 1: third TMA coordinate / bias offset = stop_layer[pair] - 1
@@ -47,271 +47,386 @@ struct TcLinParams {
   unsigned int* dbg;
 };
 
-__device__ __forceinline__ void split_store(__nv_bfloat16* hi, __nv_bfloat16* lo, const float (&v)[32]) {
-  uint32_t ph[16], pl[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-    ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    if (lo) {
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-      const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-      pl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    }
+// ------------------------------------------------------------------------------------------------
+// Persistent kernel: grid = #SMs, every CTA walks the tile list (n-tile fastest, so neighbouring CTAs
+// share A tiles in L2).  320 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-9
+// epilogue.  With one 256-column accumulator slot per tile TMEM holds two accumulators, so the epilogue
+// of tile i overlaps the MMAs of tile i+1; the LayerNorm variant needs all 512 columns for one tile.
+// Epilogue data path: TMEM -> registers (one row per thread) -> per-warp 32x32 fp32 staging tile in
+// shared memory (XOR-swizzled, conflict-free both ways) -> registers in a row-contiguous layout (8 lanes
+// x 16 B per row) -> coalesced global loads / stores.
+// ------------------------------------------------------------------------------------------------
+constexpr int EPI_WARPS = 8;
+constexpr int LIN_THREADS = 64 + EPI_WARPS * 32;
+constexpr int STG_FLOATS = 32 * 32;
+
+template <int NSLOT>
+struct LinCfg {
+  static constexpr int STAGES = NSLOT == 1 ? 3 : 2;
+  static constexpr int NBUF = NSLOT == 1 ? 2 : 1;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + NSLOT * W_TILE_BYTES;
+  static constexpr int COLS = NSLOT * BN;
+  static constexpr int VEC_BYTES = 3 * COLS * 4;            // bias | ln gamma | ln beta
+  static constexpr int LNP_BYTES = 128 * 2 * 8;             // LayerNorm partial (sum, sumsq) per row per column half
+  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_WARPS * STG_FLOATS * 4 + VEC_BYTES + LNP_BYTES + 256 + 1024;
+};
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps
+
+__device__ __forceinline__ uint2 pack_bf16x4(const float4& v, uint2* lo) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
+  const __nv_bfloat16 h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+  uint2 hi;
+  hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  hi.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+  if (lo) {
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
+    const __nv_bfloat16 l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+    lo->x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    lo->y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
   }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    reinterpret_cast<uint4*>(hi)[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-    if (lo) reinterpret_cast<uint4*>(lo)[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-  }
+  return hi;
 }
 
-__device__ __forceinline__ int n_tile_of(int bx) { return bx; }
-
-template <int NSLOT, int STAGES>
-__global__ void __launch_bounds__(192, NSLOT == 1 ? 2 : 1) tc_linear_kernel(const __grid_constant__ TcLinParams p) {
-  constexpr int STAGE_BYTES = A_TILE_BYTES + NSLOT * W_TILE_BYTES;
-  constexpr int TMEM_COLS = NSLOT * BN;
+struct TileInfo {
+  int s, r0, n_tile, sel, len;
+  long grow0;
+};
+// decode tile t (n-tile fastest); returns false for tiles with nothing to do
+__device__ __forceinline__ bool decode_tile(const TcLinParams& p, int t, int n_tiles, TileInfo& ti) {
   const int tiles_per_seq = p.st.Lp / BM;
-  const int s = blockIdx.y / tiles_per_seq;
-  const int r0 = (blockIdx.y % tiles_per_seq) * BM;
-  const int len = p.st.len[s];
-  if (r0 >= len) return;
-  const int pair = s >= p.st.B ? s - p.st.B : s;
+  ti.n_tile = t % n_tiles;
+  const int rt = t / n_tiles;
+  ti.s = rt / tiles_per_seq;
+  ti.r0 = (rt % tiles_per_seq) * BM;
+  ti.len = p.st.len[ti.s];
+  if (ti.r0 >= ti.len) return false;
+  const int pair = ti.s >= p.st.B ? ti.s - p.st.B : ti.s;
   const int sl = p.st.stop_layer[pair];
-  int sel = 0;
-  if (p.w_select == 1) sel = sl - 1;
-  else if (p.w_select == 2) sel = s >= p.st.B ? s - p.st.B : s + p.st.B;
-  else if (sl != 0) return;  // pair already exited (lightglue.py:549-550)
-  if (p.w_select == 2 && n_tile_of(blockIdx.x) * BN >= p.st.len[sel]) return;  // no live columns in this tile
+  ti.sel = 0;
+  if (p.w_select == 1) ti.sel = sl - 1;
+  else if (p.w_select == 2) {
+    ti.sel = ti.s >= p.st.B ? ti.s - p.st.B : ti.s + p.st.B;
+    if (ti.n_tile * BN >= p.st.len[ti.sel]) return false;  // no live columns
+  } else if (sl != 0) return false;                        // pair already exited (lightglue.py:549-550)
+  ti.grow0 = (long)ti.s * p.st.Lp + ti.r0;
+  return true;
+}
 
+template <int NSLOT>
+__global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_constant__ TcLinParams p) {
+  using C = LinCfg<NSLOT>;
+  constexpr int STAGES = C::STAGES, NBUF = C::NBUF, STAGE_BYTES = C::STAGE_BYTES, COLS = C::COLS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* stg_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  float* s_bias = stg_all + EPI_WARPS * STG_FLOATS;
+  float* s_gamma = s_bias + COLS;
+  float* s_beta = s_gamma + COLS;
+  float2* s_lnp = reinterpret_cast<float2*>(s_beta + COLS);  // [2 halves][128 rows]
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_lnp) + C::LNP_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_empty = acc_full + NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NBUF);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int n_tile = blockIdx.x;
-  const long grow0 = (long)s * p.st.Lp + r0;
+  const int n_tiles = p.n_tiles;
+  const int total_tiles = n_tiles * p.st.S * (p.st.Lp / BM);
   const int iters = p.passes * p.kb_total;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_hi[0]);
     tma_prefetch_desc(&p.w_hi);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < NBUF; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (p.epi == TEPI_LN_GELU && warp >= 2) {
+    for (int i = threadIdx.x - 64; i < COLS; i += EPI_WARPS * 32) { s_gamma[i] = p.ln_g[i]; s_beta[i] = p.ln_b[i]; }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (elect_one()) {  // (elect.sync lets ptxas issue the TMA / MMA instructions without a per-lane loop)
-      for (int it = 0; it < iters; ++it) {
-        const int stage = it % STAGES, round = it / STAGES;
-        mbar_wait(&empty[stage], (round & 1) ^ 1, p.dbg, 17);
-        const int pass = it / p.kb_total, kb = it % p.kb_total;
-        // pass order (x3): A_lo*W_hi, A_hi*W_lo, A_hi*W_hi ; (bf16): A_hi*W_hi
-        const bool a_lo = (p.passes == 3) && pass == 0;
-        const bool w_lo = (p.passes == 3) && pass == 1;
-        const int seg = kb >= p.kb0 ? 1 : 0;
-        const int kc = (seg ? kb - p.kb0 : kb) * BK;
-        uint8_t* sa = smem + stage * STAGE_BYTES;
-        mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-        tma_load_2d(sa, a_lo ? &p.a_lo[seg] : &p.a_hi[seg], kc, (int)grow0, &full[stage]);
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int g = 0;  // global k-block counter across tiles (ring position)
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        TileInfo ti;
+        if (!decode_tile(p, t, n_tiles, ti)) continue;
+        for (int it = 0; it < iters; ++it, ++g) {
+          const int stage = g % STAGES, round = g / STAGES;
+          mbar_wait(&empty[stage], (round & 1) ^ 1, p.dbg, 17, it);
+          const int pass = it / p.kb_total, kb = it % p.kb_total;
+          // pass order (x3): A_lo*W_hi, A_hi*W_lo, A_hi*W_hi ; (bf16): A_hi*W_hi
+          const bool a_lo = (p.passes == 3) && pass == 0;
+          const bool w_lo = (p.passes == 3) && pass == 1;
+          const int seg = kb >= p.kb0 ? 1 : 0;
+          const int kc = (seg ? kb - p.kb0 : kb) * BK;
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          tma_load_2d(sa, a_lo ? &p.a_lo[seg] : &p.a_hi[seg], kc, (int)ti.grow0, &full[stage]);
 #pragma unroll
-        for (int sl_ = 0; sl_ < NSLOT; ++sl_)
-          tma_load_3d(sa + A_TILE_BYTES + sl_ * W_TILE_BYTES, w_lo ? &p.w_lo : &p.w_hi, kb * BK,
-                      (n_tile * NSLOT + sl_) * BN, sel, &full[stage]);
+          for (int sl_ = 0; sl_ < NSLOT; ++sl_)
+            tma_load_3d(sa + A_TILE_BYTES + sl_ * W_TILE_BYTES, w_lo ? &p.w_lo : &p.w_hi, kb * BK,
+                        (ti.n_tile * NSLOT + sl_) * BN, ti.sel, &full[stage]);
+        }
       }
     }
   } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc(BM, BN, true);
-    for (int it = 0; it < iters; ++it) {
-      const int stage = it % STAGES, round = it / STAGES;
-      mbar_wait(&full[stage], round & 1, p.dbg, 18);
+    int g = 0, li = 0;  // li: index among this CTA's live tiles
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      TileInfo ti;
+      if (!decode_tile(p, t, n_tiles, ti)) continue;
+      const int buf = li % NBUF;
+      mbar_wait(&acc_empty[buf], ((li / NBUF) & 1) ^ 1, p.dbg, 20, li);  // epilogue has drained this accumulator
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint64_t adesc = make_sdesc_sw128(sa);
+      const uint32_t acc = tmem_base + buf * BN;
+      for (int it = 0; it < iters; ++it, ++g) {
+        const int stage = g % STAGES, round = g / STAGES;
+        mbar_wait(&full[stage], round & 1, p.dbg, 18, it);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = make_sdesc_sw128(sa);
 #pragma unroll
-        for (int sl_ = 0; sl_ < NSLOT; ++sl_) {
-          const uint64_t bdesc = make_sdesc_sw128(sa + A_TILE_BYTES + sl_ * W_TILE_BYTES);
+          for (int sl_ = 0; sl_ < NSLOT; ++sl_) {
+            const uint64_t bdesc = make_sdesc_sw128(sa + A_TILE_BYTES + sl_ * W_TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            mma_ss(tmem_base + sl_ * BN, sdesc_advance_k(adesc, k * 16), sdesc_advance_k(bdesc, k * 16), idesc,
-                   (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              mma_ss(acc + sl_ * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          mma_commit(&empty[stage]);
+          if (it == iters - 1) mma_commit(&acc_full[buf]);
         }
-        mma_commit(&empty[stage]);
-        if (it == iters - 1) mma_commit(acc_full);
+        __syncwarp();
       }
-      __syncwarp();
+      ++li;
     }
   } else {
-    // ------------------------------------------------------------------ epilogue
-    const int quarter = warp % 4;
-    const int row = quarter * 32 + lane;          // row inside the tile == TMEM lane
-    const int r = r0 + row;                       // row inside the sequence
-    const bool live = r < len;                    // padding rows are never written
-    const long grow = grow0 + row;
-    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const float* bias = p.bias + (p.w_select == 1 ? (long)sel * p.bias_sel_stride : 0);
-    mbar_wait(acc_full, 0, p.dbg, 19);
-    tc_fence_after();
-    uint32_t raw[32];
-    float v[32];
-    if (p.epi == TEPI_LSE || p.epi == TEPI_ARGMAX) {
-      // Assignment sweeps (lightglue.py:265-277, 302-305) on a 128 x 256 tile of S = p_s p_partner^T.  One row
-      // per thread, so every row reduction is thread-local; the transposed problem (partner as rows) is a
-      // second launch row, which makes the column reductions of the reference row reductions too.
-      const int ncols = p.st.len[sel] - n_tile * BN;  // live columns of this tile (> 0)
-      if (p.epi == TEPI_LSE) {
-        float m = -INFINITY, se = 0.f;  // online (max, sum-exp) over the tile's live columns
-        for (int c0 = 0; c0 < BN && c0 < ncols; c0 += 32) {
-          tmem_ld32(tlane + c0, raw);
-          tmem_ld_wait();
-          float cm = -INFINITY;
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int ew = warp - 2;
+    const int quarter = warp % 4;                 // TMEM lane group this warp may read
+    const int half = ew / 4;                      // which half of the tile's columns this warp owns
+    constexpr int HCOLS = COLS / 2;               // columns per warp
+    const int te = threadIdx.x - 64;              // 0..255
+    float* stg = stg_all + ew * STG_FLOATS;
+    const int row = quarter * 32 + lane;          // accumulator row of this thread (row-per-thread phase)
+    const int crow = lane >> 3, cc4 = lane & 7;   // coalesced phase: row-in-group-of-4, 16-byte column chunk
+    int li = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      TileInfo ti;
+      if (!decode_tile(p, t, n_tiles, ti)) continue;
+      const int buf = li % NBUF;
+      const float* bias = p.bias + (p.w_select == 1 ? (long)ti.sel * p.bias_sel_stride : 0) + ti.n_tile * COLS;
+      epi_bar();  // previous tile's readers of s_bias / s_lnp are done
+      if (p.epi != TEPI_LSE && p.epi != TEPI_ARGMAX)
+        for (int i = te; i < COLS; i += EPI_WARPS * 32) s_bias[i] = bias[i];
+      epi_bar();
+      mbar_wait(&acc_full[buf], (li / NBUF) & 1, p.dbg, 19, li);
+      tc_fence_after();
+      const uint32_t tl = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16) + half * HCOLS;
+      const int r = ti.r0 + row;
+      const bool live = r < ti.len;
+      const long grow = ti.grow0 + row;
+      uint32_t raw[32];
+
+      if (p.epi == TEPI_LSE || p.epi == TEPI_ARGMAX) {
+        // Assignment sweeps (lightglue.py:265-277, 302-305) on a 128 x 256 tile of S = p_s p_partner^T; every
+        // row reduction is thread-local, the transposed problem (partner as rows) is just another tile row.
+        const int ncols = p.st.len[ti.sel] - ti.n_tile * BN - half * HCOLS;  // live columns of this warp's half
+        const int slot = ti.n_tile * 2 + half;
+        if (p.epi == TEPI_LSE) {
+          float m = -INFINITY, se = 0.f;  // online (max, sum-exp)
+          for (int c0 = 0; c0 < HCOLS && c0 < ncols; c0 += 32) {
+            tmem_ld32(tl + c0, raw);
+            tmem_ld_wait();
+            float cm = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = (c0 + j < ncols) ? __uint_as_float(raw[j]) : -INFINITY;
-            cm = fmaxf(cm, v[j]);
+            for (int j = 0; j < 32; ++j) {
+              if (c0 + j >= ncols) raw[j] = 0xff800000u;
+              cm = fmaxf(cm, __uint_as_float(raw[j]));
+            }
+            if (cm > m) { se *= expf(m - cm); m = cm; }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) se += expf(__uint_as_float(raw[j]) - m);
           }
-          if (cm > m) { se *= expf(m - cm); m = cm; }
+          if (live) reinterpret_cast<float2*>(p.part)[grow * p.part_stride + slot] = make_float2(m, se);
+        } else {
+          // score = 2 S + term_s[i] + term_partner[j]; the row term does not move the arg-max
+          const float* ct = p.term + (long)ti.sel * p.st.Lp + ti.n_tile * BN + half * HCOLS;
+          float best = -INFINITY; int arg = 0;
+          for (int c0 = 0; c0 < HCOLS && c0 < ncols; c0 += 32) {
+            tmem_ld32(tl + c0, raw);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) se += expf(v[j] - m);
-        }
-        if (live) {
-          float2* o = reinterpret_cast<float2*>(p.part) + grow * p.part_stride + n_tile;
-          *o = make_float2(m, se);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 c4v = __ldg(reinterpret_cast<const float4*>(ct + c0) + j4);
+              const float cc[4] = {c4v.x, c4v.y, c4v.z, c4v.w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = j4 * 4 + jj;
+                const float sc = fmaf(2.f, __uint_as_float(raw[j]), cc[jj]);
+                if (c0 + j < ncols && sc > best) { best = sc; arg = ti.n_tile * BN + half * HCOLS + c0 + j; }  // first max wins
+              }
+            }
+          }
+          if (live) {
+            p.part[grow * p.part_stride + slot] = best + p.term[grow];
+            p.part_arg[grow * p.part_stride + slot] = arg;
+          }
         }
       } else {
-        // score = 2 S + term_s[i] + term_partner[j]; the row term is constant per thread and does not move the arg-max
-        const float* ct = p.term + (long)sel * p.st.Lp + n_tile * BN;
-        float best = -INFINITY; int arg = 0;
-        for (int c0 = 0; c0 < BN && c0 < ncols; c0 += 32) {
-          tmem_ld32(tlane + c0, raw);
+        float mean = 0.f, rstd = 1.f;
+        if (p.epi == TEPI_LN_GELU) {
+          // LayerNorm(512, eps 1e-5) statistics (lightglue.py:154): shifted single sweep over this warp's half
+          // of the row, halves combined through shared memory
+          float sh = 0.f, s1 = 0.f, s2 = 0.f;
+          for (int c0 = 0; c0 < HCOLS; c0 += 32) {
+            tmem_ld32(tl + c0, raw);
+            tmem_ld_wait();
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + half * HCOLS + c0);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = b4[j4];
+              const float v0 = __uint_as_float(raw[4 * j4]) + bb.x, v1 = __uint_as_float(raw[4 * j4 + 1]) + bb.y;
+              const float v2 = __uint_as_float(raw[4 * j4 + 2]) + bb.z, v3 = __uint_as_float(raw[4 * j4 + 3]) + bb.w;
+              if (c0 == 0 && j4 == 0) sh = v0;  // shift by the first element: cancellation-free E[(v-sh)^2]
+              const float d0 = v0 - sh, d1 = v1 - sh, d2 = v2 - sh, d3 = v3 - sh;
+              s1 += (d0 + d1) + (d2 + d3);
+              s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
+            }
+          }
+          // this half: mean_h = sh + s1/H, M2_h = sum (v - mean_h)^2 = s2 - s1^2/H (shifted -> no cancellation);
+          // halves merge with Chan's formula: M2 = M2_a + M2_b + (mean_a - mean_b)^2 * H / 2
+          const float mh = sh + s1 * (1.f / HCOLS);
+          s_lnp[half * 128 + row] = make_float2(mh, s2 - s1 * s1 * (1.f / HCOLS));
+          epi_bar();
+          const float2 a = s_lnp[row], b = s_lnp[128 + row];
+          mean = 0.5f * (a.x + b.x);
+          const float dm = a.x - b.x;
+          const float var = fmaxf((a.y + b.y + dm * dm * (0.5f * HCOLS)) * (1.f / COLS), 0.f);
+          rstd = rsqrtf(var + 1e-5f);
+        }
+        for (int c0 = 0; c0 < HCOLS; c0 += 32) {
+          const int tcol = half * HCOLS + c0;          // column inside the tile
+          const int col = ti.n_tile * COLS + tcol;     // output channel of element 0 of this chunk
+          tmem_ld32(tl + c0, raw);
           tmem_ld_wait();
+          // ---- row-per-thread: bias (+ scale / normalisation), then into the staging tile
+          bool direct_v = false;
+          int which = 0, hh = 0, d0 = 0;
+          if (p.epi == TEPI_QKV) {
+            // packed channel order: [q | k | v] (self) or [qk | v] (cross), each head-major h*64 + d
+            which = col / LG_DIM; hh = (col % LG_DIM) / LG_HDIM; d0 = col % LG_HDIM;
+            direct_v = p.rope ? (which == 2) : (which == 1);
+          }
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + tcol);
+          if (direct_v) {
+            // V is stored transposed [S, H, 64, Lp] (K-major B operand of P*V): 32 lanes = 32 consecutive rows
+            if (live) {
+              __half* dst = p.vt + (((long)ti.s * LG_HEADS + hh) * LG_HDIM + d0) * p.st.Lp + r;
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 bb = b4[j4];
+                dst[(long)(4 * j4) * p.st.Lp] = __float2half_rn(__uint_as_float(raw[4 * j4]) + bb.x);
+                dst[(long)(4 * j4 + 1) * p.st.Lp] = __float2half_rn(__uint_as_float(raw[4 * j4 + 1]) + bb.y);
+                dst[(long)(4 * j4 + 2) * p.st.Lp] = __float2half_rn(__uint_as_float(raw[4 * j4 + 2]) + bb.z);
+                dst[(long)(4 * j4 + 3) * p.st.Lp] = __float2half_rn(__uint_as_float(raw[4 * j4 + 3]) + bb.w);
+              }
+            }
+            continue;
+          }
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 c4 = __ldg(reinterpret_cast<const float4*>(ct + c0) + j4);
-            const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int j = j4 * 4 + jj;
-              const float sc = fmaf(2.f, __uint_as_float(raw[j]), cc[jj]);
-              if (c0 + j < ncols && sc > best) { best = sc; arg = n_tile * BN + c0 + j; }  // first max wins ties
+            const float4 bb = b4[j4];
+            float4 v;
+            v.x = __uint_as_float(raw[4 * j4]) + bb.x; v.y = __uint_as_float(raw[4 * j4 + 1]) + bb.y;
+            v.z = __uint_as_float(raw[4 * j4 + 2]) + bb.z; v.w = __uint_as_float(raw[4 * j4 + 3]) + bb.w;
+            if (p.epi == TEPI_LN_GELU) {
+              v.x = (v.x - mean) * rstd; v.y = (v.y - mean) * rstd; v.z = (v.z - mean) * rstd; v.w = (v.w - mean) * rstd;
+            } else {
+              v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
             }
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) = v;
           }
-        }
-        if (live) {
-          p.part[grow * p.part_stride + n_tile] = best + p.term[grow];
-          p.part_arg[grow * p.part_stride + n_tile] = arg;
-        }
-      }
-    } else if (p.epi == TEPI_LN_GELU) {
-      // LayerNorm(512, eps 1e-5) + exact GELU (lightglue.py:154-155): three sweeps over the TMEM row
-      float sum = 0.f;
-      for (int c0 = 0; c0 < NSLOT * BN; c0 += 32) {
-        tmem_ld32(tlane + c0, raw);
-        tmem_ld_wait();
+          __syncwarp();
+          // ---- row-contiguous phase: 4 rows x 128 B per warp instruction
+          const int ccol = col + cc4 * 4;  // first of this lane's 4 output channels
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum += __uint_as_float(raw[j]) + __ldg(bias + c0 + j);
-      }
-      const float mean = sum * (1.f / (NSLOT * BN));
-      float var = 0.f;
-      for (int c0 = 0; c0 < NSLOT * BN; c0 += 32) {
-        tmem_ld32(tlane + c0, raw);
-        tmem_ld_wait();
+          for (int itr = 0; itr < 8; ++itr) {
+            const int lr = itr * 4 + crow;                       // row inside the warp's 32
+            const int rr = ti.r0 + quarter * 32 + lr;            // row inside the sequence
+            float4 v = *reinterpret_cast<const float4*>(stg + lr * 32 + ((cc4 ^ (lr & 7)) << 2));
+            if (rr >= ti.len) continue;                          // padding rows are never written
+            const long gr = ti.grow0 + quarter * 32 + lr;
+            if (p.epi == TEPI_LN_GELU) {
+              const float4 g = *reinterpret_cast<const float4*>(s_gamma + tcol + cc4 * 4);
+              const float4 be = *reinterpret_cast<const float4*>(s_beta + tcol + cc4 * 4);
+              float y[4] = {fmaf(v.x, g.x, be.x), fmaf(v.y, g.y, be.y), fmaf(v.z, g.z, be.z), fmaf(v.w, g.w, be.w)};
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float d = __uint_as_float(raw[j]) + __ldg(bias + c0 + j) - mean;
-          var = fmaf(d, d, var);
-        }
-      }
-      const float rstd = rsqrtf(var * (1.f / (NSLOT * BN)) + 1e-5f);
-      for (int c0 = 0; c0 < NSLOT * BN; c0 += 32) {
-        tmem_ld32(tlane + c0, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float y = (__uint_as_float(raw[j]) + __ldg(bias + c0 + j) - mean) * rstd * __ldg(p.ln_g + c0 + j) +
-                          __ldg(p.ln_b + c0 + j);
-          v[j] = 0.5f * y * (1.f + erff(y * 0.70710678118654752f));
-        }
-        if (live) split_store(p.out_h + grow * p.ldb + c0, p.out_l ? p.out_l + grow * p.ldb + c0 : nullptr, v);
-      }
-    } else {
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        tmem_ld32(tlane + c0, raw);
-        tmem_ld_wait();
-        const int col = n_tile * BN + c0;  // output channel of v[0]
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(raw[j]) + __ldg(bias + col + j)) * p.scale;
-        if (p.epi == TEPI_QKV) {
-          // packed channel order: [q | k | v] (self) or [qk | v] (cross), each head-major h*64 + d
-          const int which = col / LG_DIM, h = (col % LG_DIM) / LG_HDIM, d0 = col % LG_HDIM;
-          const bool is_v = p.rope ? (which == 2) : (which == 1);
-          if (!is_v) {
-            if (p.rope && live) {  // rotary embedding (lightglue.py:58-65, 168-169); freq index = d / 2
-              const float* csr = p.cs + grow * 64 + d0 / 2;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float c = csr[j], sn = csr[32 + j];
-                const float a = v[2 * j], b = v[2 * j + 1];
-                v[2 * j] = a * c - b * sn;
-                v[2 * j + 1] = b * c + a * sn;
+              for (int e = 0; e < 4; ++e) y[e] = 0.5f * y[e] * (1.f + erff(y[e] * 0.70710678118654752f));  // exact GELU
+              uint2 lo;
+              const uint2 hi = pack_bf16x4(make_float4(y[0], y[1], y[2], y[3]), p.out_l ? &lo : nullptr);
+              *reinterpret_cast<uint2*>(p.out_h + gr * p.ldb + ccol) = hi;
+              if (p.out_l) *reinterpret_cast<uint2*>(p.out_l + gr * p.ldb + ccol) = lo;
+            } else if (p.epi == TEPI_BF16) {
+              uint2 lo;
+              const uint2 hi = pack_bf16x4(v, p.out_l ? &lo : nullptr);
+              *reinterpret_cast<uint2*>(p.out_h + gr * p.ldb + ccol) = hi;
+              if (p.out_l) *reinterpret_cast<uint2*>(p.out_l + gr * p.ldb + ccol) = lo;
+            } else if (p.epi == TEPI_RESID) {  // x + ffn(...) (lightglue.py:172 / 228-229)
+              float4* xo = reinterpret_cast<float4*>(p.out_f32 + gr * p.ldo + ccol);
+              const float4 x = *xo;
+              v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+              *xo = v;
+              uint2 lo;
+              const uint2 hi = pack_bf16x4(v, p.out_l ? &lo : nullptr);
+              *reinterpret_cast<uint2*>(p.out_h + gr * p.ldb + ccol) = hi;
+              if (p.out_l) *reinterpret_cast<uint2*>(p.out_l + gr * p.ldb + ccol) = lo;
+            } else if (p.epi == TEPI_F32) {
+              *reinterpret_cast<float4*>(p.out_f32 + gr * p.ldo + ccol) = v;
+              if (p.out_h) {
+                uint2 lo;
+                const uint2 hi = pack_bf16x4(v, p.out_l ? &lo : nullptr);
+                *reinterpret_cast<uint2*>(p.out_h + gr * p.ldb + ccol) = hi;
+                if (p.out_l) *reinterpret_cast<uint2*>(p.out_l + gr * p.ldb + ccol) = lo;
               }
-            }
-            if (live) {
-              __half* dst = (which == 0 ? p.q : p.k) + (((long)s * LG_HEADS + h) * p.st.Lp + r) * LG_HDIM + d0;
-              uint32_t pk[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const __half2 t = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-                pk[j] = *reinterpret_cast<const uint32_t*>(&t);
+            } else {  // TEPI_QKV, q or k
+              const int d = d0 + cc4 * 4;
+              if (p.rope) {  // rotary embedding (lightglue.py:58-65, 168-169); freq index = d / 2
+                const float* csr = p.cs + gr * 64 + d / 2;
+                const float2 c2 = *reinterpret_cast<const float2*>(csr), s2 = *reinterpret_cast<const float2*>(csr + 32);
+                const float a0 = v.x, a1 = v.y, a2 = v.z, a3 = v.w;
+                v.x = a0 * c2.x - a1 * s2.x; v.y = a1 * c2.x + a0 * s2.x;
+                v.z = a2 * c2.y - a3 * s2.y; v.w = a3 * c2.y + a2 * s2.y;
               }
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                reinterpret_cast<uint4*>(dst)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              __half* dst = (which == 0 ? p.q : p.k) + (((long)ti.s * LG_HEADS + hh) * p.st.Lp + rr) * LG_HDIM + d;
+              const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+              uint2 pk;
+              pk.x = *reinterpret_cast<const uint32_t*>(&h01); pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+              *reinterpret_cast<uint2*>(dst) = pk;
             }
-          } else if (live) {  // V is stored transposed [S, H, 64, Lp] so that P*V sees a K-major B operand
-            __half* dst = p.vt + (((long)s * LG_HEADS + h) * LG_HDIM + d0) * p.st.Lp + r;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dst[(long)j * p.st.Lp] = __float2half_rn(v[j]);
           }
-        } else if (p.epi == TEPI_BF16) {
-          if (live) split_store(p.out_h + grow * p.ldb + col, p.out_l ? p.out_l + grow * p.ldb + col : nullptr, v);
-        } else if (p.epi == TEPI_RESID) {  // x + ffn(...) (lightglue.py:172 / 228-229)
-          if (live) {
-            float4* xo = reinterpret_cast<float4*>(p.out_f32 + grow * p.ldo + col);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 x = xo[j];
-              x.x += v[4 * j]; x.y += v[4 * j + 1]; x.z += v[4 * j + 2]; x.w += v[4 * j + 3];
-              xo[j] = x;
-              v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
-            }
-            split_store(p.out_h + grow * p.ldb + col, p.out_l ? p.out_l + grow * p.ldb + col : nullptr, v);
-          }
-        } else {  // TEPI_F32
-          if (live) {
-            float4* xo = reinterpret_cast<float4*>(p.out_f32 + grow * p.ldo + col);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) xo[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            if (p.out_h) split_store(p.out_h + grow * p.ldb + col, p.out_l ? p.out_l + grow * p.ldb + col : nullptr, v);
-          }
+          __syncwarp();
         }
       }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      ++li;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
 // fp32 -> bf16 hi (/ lo) for rows < len
@@ -434,17 +549,24 @@ int wmap(LgHandle* h, CUtensorMap* out, const void* base, uint64_t Nout, uint64_
   return 0;
 }
 
-template <int NSLOT, int STAGES>
-int launch_linear(const TcLinParams& p, int n_tiles, cudaStream_t stream) {
-  constexpr int smem = STAGES * (A_TILE_BYTES + NSLOT * W_TILE_BYTES) + 1024 + 256;
+int g_num_sms = 0;
+template <int NSLOT>
+int launch_linear(TcLinParams& p, int n_tiles, cudaStream_t stream) {
+  constexpr int smem = LinCfg<NSLOT>::SMEM;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<NSLOT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
     attr = true;
   }
-  dim3 grid(n_tiles, p.st.S * (p.st.Lp / BM));
-  tc_linear_kernel<NSLOT, STAGES><<<grid, 192, smem, stream>>>(p);
+  p.n_tiles = n_tiles;
+  const int total = n_tiles * p.st.S * (p.st.Lp / BM);
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  tc_linear_kernel<NSLOT><<<grid, LIN_THREADS, smem, stream>>>(p);
   LG_CHECK_LAUNCH();
   return 0;
 }
@@ -480,8 +602,8 @@ int run_linear(LgHandle* h, const SeqState& st, const LinDesc& d, TcLinParams& p
   if (p.w_select != 2) p.w_select = d.nsel > 1;
   p.dbg = h->tc.dbg;
   h->launches += 1;
-  if (p.epi == TEPI_LN_GELU) return launch_linear<2, 2>(p, 1, stream);
-  return launch_linear<1, 2>(p, d.nout / BN, stream);
+  if (p.epi == TEPI_LN_GELU) return launch_linear<2>(p, 1, stream);
+  return launch_linear<1>(p, d.nout / BN, stream);
 }
 }  // namespace
 
@@ -499,7 +621,7 @@ __global__ void assign_lse_combine_kernel(const float* __restrict__ part, const 
   const int s = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= st.len[s]) return;
   const int partner = s >= st.B ? s - st.B : s + st.B;
-  const int nt = (st.len[partner] + BN - 1) / BN;
+  const int nt = (st.len[partner] + BN / 2 - 1) / (BN / 2);  // 128-column slots (two per tile)
   const float2* pt = reinterpret_cast<const float2*>(part) + ((long)s * st.Lp + r) * ntc;
   float m = -INFINITY;
   for (int t = 0; t < nt; ++t) m = fmaxf(m, pt[t].x);
@@ -514,7 +636,7 @@ __global__ void assign_best_combine_kernel(const float* __restrict__ part, const
   const int s = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= st.len[s]) return;
   const int partner = s >= st.B ? s - st.B : s + st.B;
-  const int nt = (st.len[partner] + BN - 1) / BN;
+  const int nt = (st.len[partner] + BN / 2 - 1) / (BN / 2);
   const long base = ((long)s * st.Lp + r) * ntc;
   float best = -INFINITY; int arg = 0;
   for (int t = 0; t < nt; ++t)
@@ -533,7 +655,7 @@ int tc_assign_sweeps(LgHandle* h, const TcBuffers& b, const SeqState& st, const 
     TcLinParams p{};
     p.epi = sweep == 0 ? TEPI_LSE : TEPI_ARGMAX;
     p.scale = 1.f; p.bias = h->wpk;  // unused
-    p.part = part; p.part_arg = part_arg; p.part_stride = ntc; p.term = term;
+    p.part = part; p.part_arg = part_arg; p.part_stride = 2 * ntc; p.term = term;
     p.w_select = 2;
     const bool x3 = h->cfg.precision == LG_PREC_BF16X3;
     const uint64_t rows = (uint64_t)st.S * st.Lp;
@@ -547,14 +669,14 @@ int tc_assign_sweeps(LgHandle* h, const TcBuffers& b, const SeqState& st, const 
     p.kb0 = LG_DIM / BK; p.kb_total = LG_DIM / BK; p.passes = x3 ? 3 : 1;
     p.st = st; p.dbg = h->tc.dbg;
     h->launches += 1;
-    if ((r = launch_linear<1, 2>(p, ntc, stream))) return r;
+    if ((r = launch_linear<1>(p, ntc, stream))) return r;
     if (sweep == 0) {
-      assign_lse_combine_kernel<<<dim3((st.Lp + 255) / 256, st.S), 256, 0, stream>>>(part, z, term, ntc, st);
+      assign_lse_combine_kernel<<<dim3((st.Lp + 255) / 256, st.S), 256, 0, stream>>>(part, z, term, 2 * ntc, st);
       LG_CHECK_LAUNCH();
       h->launches += 1;
     }
   }
-  assign_best_combine_kernel<<<dim3((st.Lp + 255) / 256, st.S), 256, 0, stream>>>(part, part_arg, ntc, rowbest, rowarg, colbest,
+  assign_best_combine_kernel<<<dim3((st.Lp + 255) / 256, st.S), 256, 0, stream>>>(part, part_arg, 2 * ntc, rowbest, rowarg, colbest,
                                                                                     colarg, nt64, st);
   LG_CHECK_LAUNCH();
   h->launches += 1;

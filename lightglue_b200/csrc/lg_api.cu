@@ -222,7 +222,8 @@ struct Workspace {
   int Lp, nt;
   float *xa, *xb, *csa, *csb, *q, *k, *v, *ctx, *msg, *hbuf, *z, *term;
   float *rowpart, *colpart, *rowlse, *collse, *rowbest, *colbest, *ms0c, *ms1c;
-  int *rowarg, *colarg, *m0c, *m1c;
+  int *rowarg, *colarg, *m0c, *m1c, *tc_parg;
+  float* tc_part;
   int *lena, *lenb, *inda, *indb, *prune, *stop_layer, *below, *pos, *did_prune;
   unsigned char* keep;
   TcBuffers tc;
@@ -260,6 +261,11 @@ void carve(const LgHandle* h, int B, int M, int N, char* base, Workspace* w) {
   }
   w->z = b.take<float>(R);
   w->term = b.take<float>(R);
+  {  // tensor-core assignment sweeps: one (max, sumexp) / (best, arg) slot per 128 columns of the partner
+    const size_t slots = fp32 ? 0 : 2 * (size_t)((Lp + 255) / 256);
+    w->tc_part = b.take<float>(R * slots * 2);
+    w->tc_parg = b.take<int>(R * slots);
+  }
   const size_t P = (size_t)B * Lp;
   w->rowpart = b.take<float>(P * w->nt * 2);
   w->colpart = b.take<float>(P * w->nt * 2);
@@ -338,7 +344,7 @@ static int run_assign(LgHandle* h, const Workspace& w, const SeqState& st, const
       // matches-only variant: both similarity sweeps on the tensor cores, nothing N x M ever reaches HBM
       RC(misc_assign_z(a, st, stream));
       h->launches += 1;
-      RC(tc_assign_sweeps(h, w.tc, st, w.z, w.rowpart, reinterpret_cast<int*>(w.colpart), w.term, w.rowbest, w.rowarg,
+      RC(tc_assign_sweeps(h, w.tc, st, w.z, w.tc_part, w.tc_parg, w.term, w.rowbest, w.rowarg,
                           w.colbest, w.colarg, w.nt, stream));
       RC(misc_assign_tail(a, st, stream, &h->launches));
     } else {
