@@ -45,6 +45,12 @@ struct TcLinParams {
   __half* q; __half* k; __half* vt; const float* cs;
   const float* ln_g; const float* ln_b;
   unsigned int* dbg;
+  // epilogue tensor maps (all boxes are 32 rows x 128 bytes, 128B swizzle)
+  CUtensorMap o_h;          // bf16 hi output [rows, ldb], box 64 cols x 32 rows, 128B swizzle (two chunks per store)
+  CUtensorMap o_l32;        // bf16 lo output, box 32 cols x 32 rows, no swizzle (one chunk per store)
+  CUtensorMap o_f32;        // fp32 output / residual [rows, 256], box 32 cols (TEPI_RESID loads and stores through it)
+  CUtensorMap o_q, o_k;     // fp16 [S*H, Lp, 64], box (64, 32, 1)
+  CUtensorMap cs_map;       // fp32 [rows, 64] cos | sin, box 32 cols
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -58,35 +64,24 @@ struct TcLinParams {
 // ------------------------------------------------------------------------------------------------
 constexpr int EPI_WARPS = 8;
 constexpr int LIN_THREADS = 64 + EPI_WARPS * 32;
-constexpr int STG_FLOATS = 32 * 32;
 
 template <int NSLOT>
 struct LinCfg {
-  static constexpr int STAGES = NSLOT == 1 ? 3 : 2;
+  static constexpr int STAGES = 2;
   static constexpr int NBUF = NSLOT == 1 ? 2 : 1;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + NSLOT * W_TILE_BYTES;
   static constexpr int COLS = NSLOT * BN;
+  // per epilogue warp: box A (4 KB: fp32 32x32 output box / rotary cos), box B (4 KB: 16-bit 32x64 box, hi or
+  // fp16), box C (4 KB: rotary sin, or the dense 32x32 bf16 "lo" box).  The LayerNorm variant has no box A.
+  static constexpr int WARP_BYTES = NSLOT == 1 ? 3 * 4096 : 4096 + 2048;
+  static constexpr int BOXB_OFF = NSLOT == 1 ? 4096 : 0;
+  static constexpr int BOXC_OFF = NSLOT == 1 ? 8192 : 4096;
   static constexpr int VEC_BYTES = 3 * COLS * 4;            // bias | ln gamma | ln beta
-  static constexpr int LNP_BYTES = 128 * 2 * 8;             // LayerNorm partial (sum, sumsq) per row per column half
-  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_WARPS * STG_FLOATS * 4 + VEC_BYTES + LNP_BYTES + 256 + 1024;
+  static constexpr int LNP_BYTES = 128 * 2 * 8;             // LayerNorm partial (mean, M2) per row per column half
+  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_WARPS * WARP_BYTES + VEC_BYTES + LNP_BYTES + 512 + 1024;
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps
-
-__device__ __forceinline__ uint2 pack_bf16x4(const float4& v, uint2* lo) {
-  const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
-  const __nv_bfloat16 h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
-  uint2 hi;
-  hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-  hi.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
-  if (lo) {
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
-    const __nv_bfloat16 l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
-    lo->x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    lo->y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
-  }
-  return hi;
-}
 
 struct TileInfo {
   int s, r0, n_tile, sel, len;
@@ -119,8 +114,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
   constexpr int STAGES = C::STAGES, NBUF = C::NBUF, STAGE_BYTES = C::STAGE_BYTES, COLS = C::COLS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* stg_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  float* s_bias = stg_all + EPI_WARPS * STG_FLOATS;
+  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;  // 1024-aligned: per-warp TMA boxes
+  float* s_bias = reinterpret_cast<float*>(epi_smem + EPI_WARPS * C::WARP_BYTES);
   float* s_gamma = s_bias + COLS;
   float* s_beta = s_gamma + COLS;
   float2* s_lnp = reinterpret_cast<float2*>(s_beta + COLS);  // [2 halves][128 rows]
@@ -128,7 +123,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
   uint64_t* acc_empty = acc_full + NBUF;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NBUF);
+  uint64_t* ldbar = acc_empty + NBUF;  // [EPI_WARPS] per-warp TMA-load barriers (residual / rotary boxes)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ldbar + EPI_WARPS);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int n_tiles = p.n_tiles;
@@ -140,6 +136,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
     tma_prefetch_desc(&p.w_hi);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < NBUF; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
+    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&ldbar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -211,22 +208,45 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
+    // Everything stays in the row-per-thread layout tcgen05.ld delivers: results are packed into 32-row x
+    // 128-byte shared-memory boxes in the 128B-swizzle pattern and leave through TMA stores; the fp32
+    // residual and the rotary tables arrive the same way through TMA loads.  No per-lane global traffic.
     const int ew = warp - 2;
     const int quarter = warp % 4;                 // TMEM lane group this warp may read
     const int half = ew / 4;                      // which half of the tile's columns this warp owns
     constexpr int HCOLS = COLS / 2;               // columns per warp
     const int te = threadIdx.x - 64;              // 0..255
-    float* stg = stg_all + ew * STG_FLOATS;
-    const int row = quarter * 32 + lane;          // accumulator row of this thread (row-per-thread phase)
-    const int crow = lane >> 3, cc4 = lane & 7;   // coalesced phase: row-in-group-of-4, 16-byte column chunk
+    uint8_t* wsm = epi_smem + ew * C::WARP_BYTES;
+    uint8_t* boxA = wsm;                          // fp32 box / cos (NSLOT == 1 only)
+    uint8_t* boxB = wsm + C::BOXB_OFF;            // 16-bit box: 32 rows x 64 elements, swizzled
+    uint8_t* boxC = wsm + C::BOXC_OFF;            // sin box (swizzled fp32) or dense bf16 lo box (32 rows x 64 B)
+    const int row = quarter * 32 + lane;          // accumulator row of this thread
+    const int sw = lane & 7;                      // swizzle key of this thread's box row
+    uint8_t* arow = boxA + lane * 128;
+    uint8_t* brow = boxB + lane * 128;
+    uint8_t* crow_sw = boxC + lane * 128;         // as a swizzled 128-byte row (sin)
+    uint8_t* crow_lo = boxC + lane * 64;          // as a dense 64-byte row (lo)
+    uint32_t ld_phase = 0;
     int li = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       TileInfo ti;
       if (!decode_tile(p, t, n_tiles, ti)) continue;
       const int buf = li % NBUF;
       const float* bias = p.bias + (p.w_select == 1 ? (long)ti.sel * p.bias_sel_stride : 0) + ti.n_tile * COLS;
+      const int grow_w = (int)ti.grow0 + quarter * 32;   // first global row of this warp
+      const bool is_sweep = p.epi == TEPI_LSE || p.epi == TEPI_ARGMAX;
+      // which output a QKV tile feeds: packed channel order [q | k | v] (self) or [qk | v] (cross)
+      const int which = ti.n_tile;  // COLS == 256 == one of q / k / v
+      const bool qkv_v = p.epi == TEPI_QKV && (p.rope ? which == 2 : which == 1);
+      const bool use_rope = p.epi == TEPI_QKV && p.rope && !qkv_v;
+      if (NSLOT == 1 && use_rope && lane == 0) {
+        tma_store_wait_read();              // boxes of the previous tile are free again
+        mbar_arrive_expect_tx(&ldbar[ew], 8192);  // cos | sin of this warp's 32 rows (shared by all heads)
+        tma_load_2d(boxA, &p.cs_map, 0, grow_w, &ldbar[ew]);
+        tma_load_2d(boxC, &p.cs_map, 32, grow_w, &ldbar[ew]);
+      }
       epi_bar();  // previous tile's readers of s_bias / s_lnp are done
-      if (p.epi != TEPI_LSE && p.epi != TEPI_ARGMAX)
+      if (!is_sweep)
         for (int i = te; i < COLS; i += EPI_WARPS * 32) s_bias[i] = bias[i];
       epi_bar();
       mbar_wait(&acc_full[buf], (li / NBUF) & 1, p.dbg, 19, li);
@@ -237,7 +257,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
       const long grow = ti.grow0 + row;
       uint32_t raw[32];
 
-      if (p.epi == TEPI_LSE || p.epi == TEPI_ARGMAX) {
+      if (is_sweep) {
         // Assignment sweeps (lightglue.py:265-277, 302-305) on a 128 x 256 tile of S = p_s p_partner^T; every
         // row reduction is thread-local, the transposed problem (partner as rows) is just another tile row.
         const int ncols = p.st.len[ti.sel] - ti.n_tile * BN - half * HCOLS;  // live columns of this warp's half
@@ -286,7 +306,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
         float mean = 0.f, rstd = 1.f;
         if (p.epi == TEPI_LN_GELU) {
           // LayerNorm(512, eps 1e-5) statistics (lightglue.py:154): shifted single sweep over this warp's half
-          // of the row, halves combined through shared memory
+          // of the row, halves merged through shared memory
           float sh = 0.f, s1 = 0.f, s2 = 0.f;
           for (int c0 = 0; c0 < HCOLS; c0 += 32) {
             tmem_ld32(tl + c0, raw);
@@ -315,104 +335,131 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
           rstd = rsqrtf(var + 1e-5f);
         }
         for (int c0 = 0; c0 < HCOLS; c0 += 32) {
+          const int ci = c0 / 32;                      // chunk index inside this warp's half
           const int tcol = half * HCOLS + c0;          // column inside the tile
           const int col = ti.n_tile * COLS + tcol;     // output channel of element 0 of this chunk
           tmem_ld32(tl + c0, raw);
-          tmem_ld_wait();
-          // ---- row-per-thread: bias (+ scale / normalisation), then into the staging tile
-          bool direct_v = false;
-          int which = 0, hh = 0, d0 = 0;
-          if (p.epi == TEPI_QKV) {
-            // packed channel order: [q | k | v] (self) or [qk | v] (cross), each head-major h*64 + d
-            which = col / LG_DIM; hh = (col % LG_DIM) / LG_HDIM; d0 = col % LG_HDIM;
-            direct_v = p.rope ? (which == 2) : (which == 1);
-          }
-          const float4* b4 = reinterpret_cast<const float4*>(s_bias + tcol);
-          if (direct_v) {
-            // V is stored transposed [S, H, 64, Lp] (K-major B operand of P*V): 32 lanes = 32 consecutive rows
-            if (live) {
-              __half* dst = p.vt + (((long)ti.s * LG_HEADS + hh) * LG_HDIM + d0) * p.st.Lp + r;
+          float4 xr[8];
+          if (NSLOT == 1 && p.epi == TEPI_RESID) {     // residual row segment (x + ffn(...), lightglue.py:172 / 228-229)
+            const float4* xp = reinterpret_cast<const float4*>(p.out_f32 + grow * p.ldo + col);
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 bb = b4[j4];
-                dst[(long)(4 * j4) * p.st.Lp] = __float2half_rn(__uint_as_float(raw[4 * j4]) + bb.x);
-                dst[(long)(4 * j4 + 1) * p.st.Lp] = __float2half_rn(__uint_as_float(raw[4 * j4 + 1]) + bb.y);
-                dst[(long)(4 * j4 + 2) * p.st.Lp] = __float2half_rn(__uint_as_float(raw[4 * j4 + 2]) + bb.z);
-                dst[(long)(4 * j4 + 3) * p.st.Lp] = __float2half_rn(__uint_as_float(raw[4 * j4 + 3]) + bb.w);
-              }
-            }
-            continue;
+            for (int j4 = 0; j4 < 8; ++j4) xr[j4] = xp[j4];
           }
+          if (lane == 0) tma_store_wait_read();        // every box of this warp may be rewritten
+          tmem_ld_wait();
+          __syncwarp();
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + tcol);
+          float v[32];
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 bb = b4[j4];
-            float4 v;
-            v.x = __uint_as_float(raw[4 * j4]) + bb.x; v.y = __uint_as_float(raw[4 * j4 + 1]) + bb.y;
-            v.z = __uint_as_float(raw[4 * j4 + 2]) + bb.z; v.w = __uint_as_float(raw[4 * j4 + 3]) + bb.w;
-            if (p.epi == TEPI_LN_GELU) {
-              v.x = (v.x - mean) * rstd; v.y = (v.y - mean) * rstd; v.z = (v.z - mean) * rstd; v.w = (v.w - mean) * rstd;
-            } else {
-              v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
-            }
-            *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) = v;
+            v[4 * j4] = __uint_as_float(raw[4 * j4]) + bb.x; v[4 * j4 + 1] = __uint_as_float(raw[4 * j4 + 1]) + bb.y;
+            v[4 * j4 + 2] = __uint_as_float(raw[4 * j4 + 2]) + bb.z; v[4 * j4 + 3] = __uint_as_float(raw[4 * j4 + 3]) + bb.w;
           }
-          __syncwarp();
-          // ---- row-contiguous phase: 4 rows x 128 B per warp instruction
-          const int ccol = col + cc4 * 4;  // first of this lane's 4 output channels
+          if (qkv_v) {
+            // V is stored transposed [S, H, 64, Lp] (K-major B operand of P*V): 32 lanes = 32 consecutive rows
+            if (live) {
+              const int hh = tcol / LG_HDIM, d0 = tcol % LG_HDIM;
+              __half* dst = p.vt + (((long)ti.s * LG_HEADS + hh) * LG_HDIM + d0) * p.st.Lp + r;
 #pragma unroll
-          for (int itr = 0; itr < 8; ++itr) {
-            const int lr = itr * 4 + crow;                       // row inside the warp's 32
-            const int rr = ti.r0 + quarter * 32 + lr;            // row inside the sequence
-            float4 v = *reinterpret_cast<const float4*>(stg + lr * 32 + ((cc4 ^ (lr & 7)) << 2));
-            if (rr >= ti.len) continue;                          // padding rows are never written
-            const long gr = ti.grow0 + quarter * 32 + lr;
-            if (p.epi == TEPI_LN_GELU) {
-              const float4 g = *reinterpret_cast<const float4*>(s_gamma + tcol + cc4 * 4);
-              const float4 be = *reinterpret_cast<const float4*>(s_beta + tcol + cc4 * 4);
-              float y[4] = {fmaf(v.x, g.x, be.x), fmaf(v.y, g.y, be.y), fmaf(v.z, g.z, be.z), fmaf(v.w, g.w, be.w)};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) y[e] = 0.5f * y[e] * (1.f + erff(y[e] * 0.70710678118654752f));  // exact GELU
-              uint2 lo;
-              const uint2 hi = pack_bf16x4(make_float4(y[0], y[1], y[2], y[3]), p.out_l ? &lo : nullptr);
-              *reinterpret_cast<uint2*>(p.out_h + gr * p.ldb + ccol) = hi;
-              if (p.out_l) *reinterpret_cast<uint2*>(p.out_l + gr * p.ldb + ccol) = lo;
-            } else if (p.epi == TEPI_BF16) {
-              uint2 lo;
-              const uint2 hi = pack_bf16x4(v, p.out_l ? &lo : nullptr);
-              *reinterpret_cast<uint2*>(p.out_h + gr * p.ldb + ccol) = hi;
-              if (p.out_l) *reinterpret_cast<uint2*>(p.out_l + gr * p.ldb + ccol) = lo;
-            } else if (p.epi == TEPI_RESID) {  // x + ffn(...) (lightglue.py:172 / 228-229)
-              float4* xo = reinterpret_cast<float4*>(p.out_f32 + gr * p.ldo + ccol);
-              const float4 x = *xo;
-              v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
-              *xo = v;
-              uint2 lo;
-              const uint2 hi = pack_bf16x4(v, p.out_l ? &lo : nullptr);
-              *reinterpret_cast<uint2*>(p.out_h + gr * p.ldb + ccol) = hi;
-              if (p.out_l) *reinterpret_cast<uint2*>(p.out_l + gr * p.ldb + ccol) = lo;
-            } else if (p.epi == TEPI_F32) {
-              *reinterpret_cast<float4*>(p.out_f32 + gr * p.ldo + ccol) = v;
-              if (p.out_h) {
-                uint2 lo;
-                const uint2 hi = pack_bf16x4(v, p.out_l ? &lo : nullptr);
-                *reinterpret_cast<uint2*>(p.out_h + gr * p.ldb + ccol) = hi;
-                if (p.out_l) *reinterpret_cast<uint2*>(p.out_l + gr * p.ldb + ccol) = lo;
-              }
-            } else {  // TEPI_QKV, q or k
-              const int d = d0 + cc4 * 4;
-              if (p.rope) {  // rotary embedding (lightglue.py:58-65, 168-169); freq index = d / 2
-                const float* csr = p.cs + gr * 64 + d / 2;
-                const float2 c2 = *reinterpret_cast<const float2*>(csr), s2 = *reinterpret_cast<const float2*>(csr + 32);
-                const float a0 = v.x, a1 = v.y, a2 = v.z, a3 = v.w;
-                v.x = a0 * c2.x - a1 * s2.x; v.y = a1 * c2.x + a0 * s2.x;
-                v.z = a2 * c2.y - a3 * s2.y; v.w = a3 * c2.y + a2 * s2.y;
-              }
-              __half* dst = (which == 0 ? p.q : p.k) + (((long)ti.s * LG_HEADS + hh) * p.st.Lp + rr) * LG_HDIM + d;
-              const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
-              uint2 pk;
-              pk.x = *reinterpret_cast<const uint32_t*>(&h01); pk.y = *reinterpret_cast<const uint32_t*>(&h23);
-              *reinterpret_cast<uint2*>(dst) = pk;
+              for (int j = 0; j < 32; ++j) dst[(long)j * p.st.Lp] = __float2half_rn(v[j]);
             }
+            continue;
+          }
+          if (p.epi == TEPI_LN_GELU) {
+            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + tcol);
+            const float4* e4 = reinterpret_cast<const float4*>(s_beta + tcol);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 g = g4[j4], be = e4[j4];
+              const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float y = fmaf((v[4 * j4 + e] - mean) * rstd, gg[e], bb[e]);
+                // exact (erf) GELU; erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): 1 MUFU.RCP + 1 MUFU.EX2
+                const float z = fabsf(y) * 0.70710678118654752f;
+                const float tt = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+                float pl = fmaf(1.061405429f, tt, -1.453152027f);
+                pl = fmaf(pl, tt, 1.421413741f); pl = fmaf(pl, tt, -0.284496736f); pl = fmaf(pl, tt, 0.254829592f);
+                const float ez = exp2f(-1.4426950408889634f * z * z);
+                const float erf_abs = fmaf(-pl * tt, ez, 1.f);
+                const float hy = 0.5f * y;
+                v[4 * j4 + e] = fmaf(copysignf(erf_abs, y), hy, hy);
+              }
+            }
+          } else if (p.scale != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+          }
+          if (NSLOT == 1 && p.epi == TEPI_RESID) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              v[4 * j4] += xr[j4].x; v[4 * j4 + 1] += xr[j4].y; v[4 * j4 + 2] += xr[j4].z; v[4 * j4 + 3] += xr[j4].w;
+            }
+          }
+          // ---- rotary embedding on q / k (lightglue.py:58-65, 168-169); freq index = d / 2
+          if (NSLOT == 1 && use_rope) {
+            if (ci == 0) { mbar_wait(&ldbar[ew], ld_phase & 1, p.dbg, 22, 0); ld_phase++; }
+            const int f0 = (tcol % LG_HDIM) / 2;  // 0 or 16
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const int chunk = (f0 >> 2) + j4;
+              const float4 c4v = *reinterpret_cast<const float4*>(arow + ((chunk ^ sw) << 4));
+              const float4 s4v = *reinterpret_cast<const float4*>(crow_sw + ((chunk ^ sw) << 4));
+              const float cc[4] = {c4v.x, c4v.y, c4v.z, c4v.w}, ss[4] = {s4v.x, s4v.y, s4v.z, s4v.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a = v[8 * j4 + 2 * e], b = v[8 * j4 + 2 * e + 1];
+                v[8 * j4 + 2 * e] = a * cc[e] - b * ss[e];
+                v[8 * j4 + 2 * e + 1] = b * cc[e] + a * ss[e];
+              }
+            }
+          }
+          const bool f32out = NSLOT == 1 && (p.epi == TEPI_RESID || p.epi == TEPI_F32);
+          const bool fp16 = p.epi == TEPI_QKV;
+          const bool has16 = fp16 || p.epi == TEPI_BF16 || p.epi == TEPI_LN_GELU || p.epi == TEPI_RESID ||
+                             (p.epi == TEPI_F32 && p.out_h != nullptr);
+          const bool haslo = has16 && !fp16 && p.out_l != nullptr;
+          if (f32out) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              *reinterpret_cast<float4*>(arow + ((j4 ^ sw) << 4)) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          }
+          if (has16) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              uint32_t wh[4], wl[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a = v[8 * j8 + 2 * e], b = v[8 * j8 + 2 * e + 1];
+                if (fp16) {
+                  const __half2 hh2 = __floats2half2_rn(a, b);
+                  wh[e] = *reinterpret_cast<const uint32_t*>(&hh2);
+                } else {
+                  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+                  wh[e] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+                  if (haslo) {
+                    const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha));
+                    const __nv_bfloat16 lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+                    wl[e] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+                  }
+                }
+              }
+              const int chunk = (ci & 1) * 4 + j8;  // 16-byte chunk inside the 64-element box row
+              *reinterpret_cast<uint4*>(brow + ((chunk ^ sw) << 4)) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+              if (haslo) *reinterpret_cast<uint4*>(crow_lo + (j8 << 4)) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (f32out) tma_store_2d(&p.o_f32, boxA, col, grow_w);
+            if (haslo) tma_store_2d(&p.o_l32, boxC, col, grow_w);
+            if (has16 && (ci & 1)) {  // the 64-element box is complete
+              if (fp16) tma_store_3d(which == 0 ? &p.o_q : &p.o_k, boxB, 0, ti.r0 + quarter * 32, ti.s * LG_HEADS + tcol / LG_HDIM);
+              else tma_store_2d(&p.o_h, boxB, col - 32, grow_w);
+            }
+            tma_store_commit();
           }
           __syncwarp();
         }
@@ -423,6 +470,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
       ++li;
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -479,7 +527,7 @@ EncodeFn get_encode() {
 }  // namespace
 
 int tc_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
-                    uint32_t box_inner, uint32_t box_outer) {
+                    uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
   EncodeFn enc = get_encode();
   if (!enc) return lg_set_error("cuTensorMapEncodeTiled unavailable");
   cuuint64_t dims[2] = {inner, outer};
@@ -488,7 +536,8 @@ int tc_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return lg_set_error("cuTensorMapEncodeTiled (2d) failed");
   return 0;
 }
@@ -549,6 +598,32 @@ int wmap(LgHandle* h, CUtensorMap* out, const void* base, uint64_t Nout, uint64_
   return 0;
 }
 
+// epilogue boxes: 2-D [rows, cols] tensors, 32-row boxes
+int omap2d(LgHandle* h, CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows, uint32_t box_cols,
+           bool swizzle) {
+  MapCache* mc = static_cast<MapCache*>(h->tc.map_cache);
+  MapKey key{base, cols, rows, (uint64_t)box_cols | ((uint64_t)swizzle << 16) | ((uint64_t)elem_bytes << 20), 7};
+  auto it = mc->m.find(key);
+  if (it != mc->m.end()) { *out = it->second; return 0; }
+  if (mc->m.size() > 4096) mc->m.clear();
+  int r = tc_make_tmap_2d(out, base, elem_bytes, cols, rows, cols * elem_bytes, box_cols, 32, swizzle);
+  if (r) return r;
+  mc->m.emplace(key, *out);
+  return 0;
+}
+// q / k fp16 [S*H, Lp, 64]: box (64, 32, 1)
+int omap_qk(LgHandle* h, CUtensorMap* out, const void* base, uint64_t Lp, uint64_t SH) {
+  MapCache* mc = static_cast<MapCache*>(h->tc.map_cache);
+  MapKey key{base, Lp, SH, 32, 9};
+  auto it = mc->m.find(key);
+  if (it != mc->m.end()) { *out = it->second; return 0; }
+  if (mc->m.size() > 4096) mc->m.clear();
+  int r = tc_make_tmap_3d(out, base, 2, 64, Lp, SH, 128, Lp * 128, 64, 32, 1);
+  if (r) return r;
+  mc->m.emplace(key, *out);
+  return 0;
+}
+
 int g_num_sms = 0;
 template <int NSLOT>
 int launch_linear(TcLinParams& p, int n_tiles, cudaStream_t stream) {
@@ -595,6 +670,14 @@ int run_linear(LgHandle* h, const SeqState& st, const LinDesc& d, TcLinParams& p
   if ((r = wmap(h, &p.w_hi, h->tc.w_hi + d.w_off, d.nout, K, d.nsel, d.sel_stride))) return r;
   p.w_lo = p.w_hi;
   if (x3 && (r = wmap(h, &p.w_lo, h->tc.w_lo + d.w_off, d.nout, K, d.nsel, d.sel_stride))) return r;
+  if (p.out_h && (r = omap2d(h, &p.o_h, p.out_h, 2, p.ldb, rows, 64, true))) return r;
+  if (p.out_l && (r = omap2d(h, &p.o_l32, p.out_l, 2, p.ldb, rows, 32, false))) return r;
+  if ((p.epi == TEPI_RESID || p.epi == TEPI_F32) && (r = omap2d(h, &p.o_f32, p.out_f32, 4, p.ldo, rows, 32, true))) return r;
+  if (p.epi == TEPI_QKV) {
+    if ((r = omap_qk(h, &p.o_q, p.q, st.Lp, (uint64_t)st.S * LG_HEADS))) return r;
+    if ((r = omap_qk(h, &p.o_k, p.k, st.Lp, (uint64_t)st.S * LG_HEADS))) return r;
+    if (p.rope && (r = omap2d(h, &p.cs_map, p.cs, 4, 64, rows, 32, true))) return r;
+  }
   p.kb0 = d.k0 / BK;
   p.kb_total = K / BK;
   p.passes = x3 ? 3 : 1;
