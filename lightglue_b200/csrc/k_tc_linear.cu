@@ -81,6 +81,16 @@ struct LinCfg {
   static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_WARPS * WARP_BYTES + VEC_BYTES + LNP_BYTES + 512 + 1024;
 };
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps
 
 struct TileInfo {
@@ -108,7 +118,7 @@ __device__ __forceinline__ bool decode_tile(const TcLinParams& p, int t, int n_t
   return true;
 }
 
-template <int NSLOT>
+template <int NSLOT, int EPI>
 __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_constant__ TcLinParams p) {
   using C = LinCfg<NSLOT>;
   constexpr int STAGES = C::STAGES, NBUF = C::NBUF, STAGE_BYTES = C::STAGE_BYTES, COLS = C::COLS;
@@ -140,7 +150,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
-  if (p.epi == TEPI_LN_GELU && warp >= 2) {
+  if (EPI == TEPI_LN_GELU && warp >= 2) {
     for (int i = threadIdx.x - 64; i < COLS; i += EPI_WARPS * 32) { s_gamma[i] = p.ln_g[i]; s_beta[i] = p.ln_b[i]; }
   }
   tc_fence_before();
@@ -234,11 +244,11 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
       const int buf = li % NBUF;
       const float* bias = p.bias + (p.w_select == 1 ? (long)ti.sel * p.bias_sel_stride : 0) + ti.n_tile * COLS;
       const int grow_w = (int)ti.grow0 + quarter * 32;   // first global row of this warp
-      const bool is_sweep = p.epi == TEPI_LSE || p.epi == TEPI_ARGMAX;
+      const bool is_sweep = EPI == TEPI_LSE || EPI == TEPI_ARGMAX;
       // which output a QKV tile feeds: packed channel order [q | k | v] (self) or [qk | v] (cross)
       const int which = ti.n_tile;  // COLS == 256 == one of q / k / v
-      const bool qkv_v = p.epi == TEPI_QKV && (p.rope ? which == 2 : which == 1);
-      const bool use_rope = p.epi == TEPI_QKV && p.rope && !qkv_v;
+      const bool qkv_v = EPI == TEPI_QKV && (p.rope ? which == 2 : which == 1);
+      const bool use_rope = EPI == TEPI_QKV && p.rope && !qkv_v;
       if (NSLOT == 1 && use_rope && lane == 0) {
         tma_store_wait_read();              // boxes of the previous tile are free again
         mbar_arrive_expect_tx(&ldbar[ew], 8192);  // cos | sin of this warp's 32 rows (shared by all heads)
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
         // row reduction is thread-local, the transposed problem (partner as rows) is just another tile row.
         const int ncols = p.st.len[ti.sel] - ti.n_tile * BN - half * HCOLS;  // live columns of this warp's half
         const int slot = ti.n_tile * 2 + half;
-        if (p.epi == TEPI_LSE) {
+        if (EPI == TEPI_LSE) {
           float m = -INFINITY, se = 0.f;  // online (max, sum-exp)
           for (int c0 = 0; c0 < HCOLS && c0 < ncols; c0 += 32) {
             tmem_ld32(tl + c0, raw);
@@ -304,7 +314,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
         }
       } else {
         float mean = 0.f, rstd = 1.f;
-        if (p.epi == TEPI_LN_GELU) {
+        if (EPI == TEPI_LN_GELU) {
           // LayerNorm(512, eps 1e-5) statistics (lightglue.py:154): shifted single sweep over this warp's half
           // of the row, halves merged through shared memory
           float sh = 0.f, s1 = 0.f, s2 = 0.f;
@@ -340,7 +350,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
           const int col = ti.n_tile * COLS + tcol;     // output channel of element 0 of this chunk
           tmem_ld32(tl + c0, raw);
           float4 xr[8];
-          if (NSLOT == 1 && p.epi == TEPI_RESID) {     // residual row segment (x + ffn(...), lightglue.py:172 / 228-229)
+          if (NSLOT == 1 && EPI == TEPI_RESID) {     // residual row segment (x + ffn(...), lightglue.py:172 / 228-229)
             const float4* xp = reinterpret_cast<const float4*>(p.out_f32 + grow * p.ldo + col);
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) xr[j4] = xp[j4];
@@ -366,7 +376,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
             }
             continue;
           }
-          if (p.epi == TEPI_LN_GELU) {
+          if (EPI == TEPI_LN_GELU) {
             const float4* g4 = reinterpret_cast<const float4*>(s_gamma + tcol);
             const float4* e4 = reinterpret_cast<const float4*>(s_beta + tcol);
 #pragma unroll
@@ -378,10 +388,10 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
                 const float y = fmaf((v[4 * j4 + e] - mean) * rstd, gg[e], bb[e]);
                 // exact (erf) GELU; erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): 1 MUFU.RCP + 1 MUFU.EX2
                 const float z = fabsf(y) * 0.70710678118654752f;
-                const float tt = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+                const float tt = rcp_approx(fmaf(0.3275911f, z, 1.f));
                 float pl = fmaf(1.061405429f, tt, -1.453152027f);
                 pl = fmaf(pl, tt, 1.421413741f); pl = fmaf(pl, tt, -0.284496736f); pl = fmaf(pl, tt, 0.254829592f);
-                const float ez = exp2f(-1.4426950408889634f * z * z);
+                const float ez = ex2_approx(-1.4426950408889634f * z * z);
                 const float erf_abs = fmaf(-pl * tt, ez, 1.f);
                 const float hy = 0.5f * y;
                 v[4 * j4 + e] = fmaf(copysignf(erf_abs, y), hy, hy);
@@ -391,7 +401,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= p.scale;
           }
-          if (NSLOT == 1 && p.epi == TEPI_RESID) {
+          if (NSLOT == 1 && EPI == TEPI_RESID) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               v[4 * j4] += xr[j4].x; v[4 * j4 + 1] += xr[j4].y; v[4 * j4 + 2] += xr[j4].z; v[4 * j4 + 3] += xr[j4].w;
@@ -415,10 +425,10 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
               }
             }
           }
-          const bool f32out = NSLOT == 1 && (p.epi == TEPI_RESID || p.epi == TEPI_F32);
-          const bool fp16 = p.epi == TEPI_QKV;
-          const bool has16 = fp16 || p.epi == TEPI_BF16 || p.epi == TEPI_LN_GELU || p.epi == TEPI_RESID ||
-                             (p.epi == TEPI_F32 && p.out_h != nullptr);
+          const bool f32out = NSLOT == 1 && (EPI == TEPI_RESID || EPI == TEPI_F32);
+          const bool fp16 = EPI == TEPI_QKV;
+          const bool has16 = fp16 || EPI == TEPI_BF16 || EPI == TEPI_LN_GELU || EPI == TEPI_RESID ||
+                             (EPI == TEPI_F32 && p.out_h != nullptr);
           const bool haslo = has16 && !fp16 && p.out_l != nullptr;
           if (f32out) {
 #pragma unroll
@@ -625,25 +635,39 @@ int omap_qk(LgHandle* h, CUtensorMap* out, const void* base, uint64_t Lp, uint64
 }
 
 int g_num_sms = 0;
-template <int NSLOT>
-int launch_linear(TcLinParams& p, int n_tiles, cudaStream_t stream) {
+template <int NSLOT, int EPI>
+int launch_linear_t(TcLinParams& p, int n_tiles, cudaStream_t stream) {
   constexpr int smem = LinCfg<NSLOT>::SMEM;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<NSLOT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+    if (g_num_sms <= 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+      if (g_num_sms <= 0) g_num_sms = 148;
+    }
     attr = true;
   }
   p.n_tiles = n_tiles;
   const int total = n_tiles * p.st.S * (p.st.Lp / BM);
   const int grid = total < g_num_sms ? total : g_num_sms;
-  tc_linear_kernel<NSLOT><<<grid, LIN_THREADS, smem, stream>>>(p);
+  tc_linear_kernel<NSLOT, EPI><<<grid, LIN_THREADS, smem, stream>>>(p);
   LG_CHECK_LAUNCH();
   return 0;
+}
+int launch_linear(TcLinParams& p, int n_tiles, cudaStream_t stream) {
+  switch (p.epi) {
+    case TEPI_QKV: return launch_linear_t<1, TEPI_QKV>(p, n_tiles, stream);
+    case TEPI_BF16: return launch_linear_t<1, TEPI_BF16>(p, n_tiles, stream);
+    case TEPI_LN_GELU: return launch_linear_t<2, TEPI_LN_GELU>(p, 1, stream);
+    case TEPI_RESID: return launch_linear_t<1, TEPI_RESID>(p, n_tiles, stream);
+    case TEPI_F32: return launch_linear_t<1, TEPI_F32>(p, n_tiles, stream);
+    case TEPI_LSE: return launch_linear_t<1, TEPI_LSE>(p, n_tiles, stream);
+    case TEPI_ARGMAX: return launch_linear_t<1, TEPI_ARGMAX>(p, n_tiles, stream);
+  }
+  return lg_set_error("launch_linear: bad epilogue");
 }
 
 struct LinDesc {
@@ -685,8 +709,7 @@ int run_linear(LgHandle* h, const SeqState& st, const LinDesc& d, TcLinParams& p
   if (p.w_select != 2) p.w_select = d.nsel > 1;
   p.dbg = h->tc.dbg;
   h->launches += 1;
-  if (p.epi == TEPI_LN_GELU) return launch_linear<2>(p, 1, stream);
-  return launch_linear<1>(p, d.nout / BN, stream);
+  return launch_linear(p, d.nout / BN, stream);
 }
 }  // namespace
 
@@ -752,7 +775,7 @@ int tc_assign_sweeps(LgHandle* h, const TcBuffers& b, const SeqState& st, const 
     p.kb0 = LG_DIM / BK; p.kb_total = LG_DIM / BK; p.passes = x3 ? 3 : 1;
     p.st = st; p.dbg = h->tc.dbg;
     h->launches += 1;
-    if ((r = launch_linear<1>(p, ntc, stream))) return r;
+    if ((r = launch_linear(p, ntc, stream))) return r;
     if (sweep == 0) {
       assign_lse_combine_kernel<<<dim3((st.Lp + 255) / 256, st.S), 256, 0, stream>>>(part, z, term, 2 * ntc, st);
       LG_CHECK_LAUNCH();
