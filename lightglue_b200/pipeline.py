@@ -1,0 +1,67 @@
+"""Host-to-device pipelining for batched matching.
+
+``LightGlue.forward`` is asynchronous on the current stream except for its single D2H read-back, so
+the H2D copy of batch i+1 (pinned host memory, separate copy stream) can overlap the kernels of
+batch i.  ``match_stream`` does exactly that with two in-flight device staging slots; results come
+back in pinned host tensors.  This is the throughput path a server fed from host memory uses (the
+reference has no equivalent: its ``match_pair`` moves one pair at a time, utils.py:150-165).
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Iterator
+
+import torch
+
+RESULT_KEYS = ("matches0", "matches1", "matching_scores0", "matching_scores1")
+
+
+def _to_device(batch: dict, device: torch.device) -> dict:
+    return {k: {kk: vv.to(device, non_blocking=True) for kk, vv in v.items()} for k, v in batch.items()}
+
+
+def match_stream(matcher, batches: Iterable[dict], device: torch.device | None = None) -> Iterator[Dict[str, torch.Tensor]]:
+    """Yield one result dict (pinned CPU tensors: matches0/1, matching_scores0/1, plus ``stop``) per host batch.
+
+    `batches` yields dicts in the matcher's input format whose tensors live in (ideally pinned) host
+    memory.  Copies run on a side stream one batch ahead of the compute stream."""
+    device = device or next(matcher.parameters()).device
+    compute = torch.cuda.current_stream(device)
+    copy = torch.cuda.Stream(device)
+    it = iter(batches)
+
+    def stage(b):
+        with torch.cuda.stream(copy):
+            dev = _to_device(b, device)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+        return dev, ev
+
+    try:
+        nxt = stage(next(it))
+    except StopIteration:
+        return
+    pending = None  # (host result dict, event) of the previous batch
+    while nxt is not None:
+        dev, ev = nxt
+        try:
+            nxt = stage(next(it))  # H2D of the following batch overlaps this batch's kernels
+        except StopIteration:
+            nxt = None
+        compute.wait_event(ev)
+        for v in dev.values():
+            for t in v.values():
+                t.record_stream(compute)
+        out = matcher(dev)
+        host = {k: torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True) for k in RESULT_KEYS}
+        for k in RESULT_KEYS:
+            host[k].copy_(out[k], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(compute)
+        host["stop"] = out["stop"]
+        if pending is not None:
+            pending[1].synchronize()
+            yield pending[0]
+        pending = (host, done)
+    if pending is not None:
+        pending[1].synchronize()
+        yield pending[0]

@@ -145,3 +145,23 @@ def test_tc_adaptive_runs_and_agrees(prec):
         diff = int((out["prune0"].cpu() != gold["prune0"]).sum())
         print(f"[{prec}] adaptive: prune0 differences {diff}/512")
         assert diff <= (4 if prec == "bf16x3" else 40)
+
+
+def test_match_stream_equals_direct_forward():
+    """The pinned-host streaming API (H2D one batch ahead on a copy stream) returns what forward returns."""
+    from lightglue_b200.pipeline import match_stream
+
+    sd = synth.make_state_dict()
+    m = LightGlue(features=None, precision="bf16x3", depth_confidence=-1, width_confidence=-1)
+    m.load_state_dict(sd, strict=False)
+    m = m.cuda()
+    batches = []
+    for i in range(3):
+        d, _ = synth.make_pair(384, b=2, seed=500 + i)
+        batches.append({k: {kk: vv.pin_memory() for kk, vv in v.items()} for k, v in d.items()})
+    direct = [m(to_cuda(b)) for b in batches]
+    streamed = list(match_stream(m, batches))
+    assert len(streamed) == 3
+    for a, b in zip(direct, streamed):
+        assert torch.equal(a["matches0"].cpu(), b["matches0"]) and torch.equal(a["matches1"].cpu(), b["matches1"])
+        assert torch.equal(a["matching_scores0"].cpu(), b["matching_scores0"])
