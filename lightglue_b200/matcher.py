@@ -69,6 +69,9 @@ class LightGlue(nn.Module):
         "weights": None,
         # extension: arithmetic of the linear layers -- "fp32" | "bf16" | "bf16x3" (see LG_PREC_*)
         "precision": "bf16x3",
+        # extension: replay the ~100 kernel launches of a forward as one CUDA graph per input shape (the
+        # kernels take ragged / pruned lengths from device memory, so the launch sequence is static)
+        "cuda_graph": False,
     }
 
     # reference lightglue.py:339-344; callers mutate it (benchmark.py:178-181)
@@ -126,6 +129,7 @@ class LightGlue(nn.Module):
         self.requires_grad_(False)
         self._handle = None  # (C handle, device index, signature of the packed weights)
         self._ws: Dict[tuple, torch.Tensor] = {}
+        self._graphs: Dict[tuple, tuple] = {}
         self.timing = False
 
     # ------------------------------------------------------------------ weights
@@ -204,6 +208,7 @@ class LightGlue(nn.Module):
         torch.cuda.current_stream(device).synchronize()  # the blob may be freed now
         self._handle = (handle, sig)
         self._ws.clear()
+        self._graphs.clear()
         return handle
 
     def _workspace(self, handle, device: torch.device, b: int, m: int, n: int) -> torch.Tensor:
@@ -279,33 +284,66 @@ class LightGlue(nn.Module):
         with torch.cuda.device(device):
             handle = self._get_handle(device)
             lib = _cabi.load()
-            ws = self._workspace(handle, device, b, m, n)
-            cap = min(m, n)
-            m0 = torch.empty(b, m, dtype=torch.int64, device=device)
-            m1 = torch.empty(b, n, dtype=torch.int64, device=device)
-            ms0 = torch.empty(b, m, dtype=torch.float32, device=device)
-            ms1 = torch.empty(b, n, dtype=torch.float32, device=device)
-            meta = torch.empty(2, b, dtype=torch.int32, device=device)  # [stop | n_matches]
-            pr0 = torch.empty(b, m, dtype=torch.int32, device=device) if prune else None
-            pr1 = torch.empty(b, n, dtype=torch.int32, device=device) if prune else None
-            pairs = torch.empty(b, cap, 2, dtype=torch.int64, device=device)
-            pscores = torch.empty(b, cap, dtype=torch.float32, device=device)
-            ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
-            inp = _cabi.LgInputs(
-                b, m, n, ptr(k0), ptr(k1), ptr(x0), ptr(x1), ptr(s0), ptr(s1), ptr(sc0), ptr(or0), ptr(sc1), ptr(or1),
-                pruning_th,
-            )
-            out = _cabi.LgOutputs(
-                ptr(m0), ptr(m1), ptr(ms0), ptr(ms1), meta[0].data_ptr(), ptr(pr0), ptr(pr1), meta[1].data_ptr(),
-                ptr(pairs), ptr(pscores), None,
-            )
-            if self.timing:
-                lib.lg_timing_enable(handle, 1)
-                self.timing = False
-            stream = torch.cuda.current_stream(device).cuda_stream
-            _cabi.check(
-                lib.lg_forward(handle, C.byref(inp), C.byref(out), ws.data_ptr(), ws.numel(), stream), "lg_forward"
-            )
+            use_graph = bool(self.conf.cuda_graph) and m > 0 and n > 0 and not self.timing
+            key = (device.index, b, m, n, prune, pruning_th, s0 is None, s1 is None)
+            slot = self._graphs.get(key) if use_graph else None
+            if slot is None:
+                ws = self._workspace(handle, device, b, m, n)
+                cap = min(m, n)
+                io = {
+                    "m0": torch.empty(b, m, dtype=torch.int64, device=device),
+                    "m1": torch.empty(b, n, dtype=torch.int64, device=device),
+                    "ms0": torch.empty(b, m, dtype=torch.float32, device=device),
+                    "ms1": torch.empty(b, n, dtype=torch.float32, device=device),
+                    "meta": torch.empty(2, b, dtype=torch.int32, device=device),  # [stop | n_matches]
+                    "pr0": torch.empty(b, m, dtype=torch.int32, device=device) if prune else None,
+                    "pr1": torch.empty(b, n, dtype=torch.int32, device=device) if prune else None,
+                    "pairs": torch.empty(b, cap, 2, dtype=torch.int64, device=device),
+                    "pscores": torch.empty(b, cap, dtype=torch.float32, device=device),
+                }
+                ins = [k0, k1, x0, x1, s0, s1, sc0, or0, sc1, or1]
+                if use_graph:  # static input buffers the graph reads from
+                    ins = [None if t is None else t.clone() for t in ins]
+                ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+                inp = _cabi.LgInputs(b, m, n, *[ptr(t) for t in ins], pruning_th)
+                out = _cabi.LgOutputs(
+                    ptr(io["m0"]), ptr(io["m1"]), ptr(io["ms0"]), ptr(io["ms1"]), io["meta"][0].data_ptr(), ptr(io["pr0"]),
+                    ptr(io["pr1"]), io["meta"][1].data_ptr(), ptr(io["pairs"]), ptr(io["pscores"]), None,
+                )
+                if self.timing:
+                    lib.lg_timing_enable(handle, 1)
+                    self.timing = False
+
+                def launch():
+                    stream = torch.cuda.current_stream(device).cuda_stream
+                    _cabi.check(
+                        lib.lg_forward(handle, C.byref(inp), C.byref(out), ws.data_ptr(), ws.numel(), stream), "lg_forward"
+                    )
+
+                if use_graph:
+                    side = torch.cuda.Stream(device)
+                    side.wait_stream(torch.cuda.current_stream(device))
+                    with torch.cuda.stream(side):
+                        launch()  # warm-up: one-time function attributes / tensor-map cache
+                    torch.cuda.current_stream(device).wait_stream(side)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        launch()
+                    slot = (graph, ins, io, (inp, out, ws))
+                    if len(self._graphs) > 16:
+                        self._graphs.clear()
+                    self._graphs[key] = slot
+                else:
+                    launch()
+            if use_graph:
+                graph, ins, io, _keep = slot
+                for dst, src in zip(ins, [k0, k1, x0, x1, s0, s1, sc0, or0, sc1, or1]):
+                    if dst is not None:
+                        dst.copy_(src, non_blocking=True)
+                graph.replay()
+                io = {k: (None if v is None else v.clone()) for k, v in io.items()}  # results must not alias the graph's buffers
+            m0, m1, ms0, ms1, meta = io["m0"], io["m1"], io["ms0"], io["ms1"], io["meta"]
+            pr0, pr1, pairs, pscores = io["pr0"], io["pr1"], io["pairs"], io["pscores"]
             meta_h = meta.cpu()  # the single device->host read-back: stop flags + match counts
 
         stop = int(meta_h[0].max())

@@ -23,7 +23,8 @@ def match_stream(matcher, batches: Iterable[dict], device: torch.device | None =
     """Yield one result dict (pinned CPU tensors: matches0/1, matching_scores0/1, plus ``stop``) per host batch.
 
     `batches` yields dicts in the matcher's input format whose tensors live in (ideally pinned) host
-    memory.  Copies run on a side stream one batch ahead of the compute stream."""
+    memory.  Copies run on a side stream one batch ahead of the compute stream.  The yielded tensors live
+    in a ring of three pinned buffers: a result stays valid until two further results have been yielded."""
     device = device or next(matcher.parameters()).device
     compute = torch.cuda.current_stream(device)
     copy = torch.cuda.Stream(device)
@@ -41,6 +42,8 @@ def match_stream(matcher, batches: Iterable[dict], device: torch.device | None =
     except StopIteration:
         return
     pending = None  # (host result dict, event) of the previous batch
+    slots = [dict(), dict(), dict()]  # ring of pinned result buffers (pinned allocation is slow: reuse)
+    n_done = 0
     while nxt is not None:
         dev, ev = nxt
         try:
@@ -52,7 +55,12 @@ def match_stream(matcher, batches: Iterable[dict], device: torch.device | None =
             for t in v.values():
                 t.record_stream(compute)
         out = matcher(dev)
-        host = {k: torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True) for k in RESULT_KEYS}
+        slot = slots[n_done % len(slots)]
+        if not slot or any(slot[k].shape != out[k].shape for k in RESULT_KEYS):
+            slot.clear()
+            slot.update({k: torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True) for k in RESULT_KEYS})
+        host = dict(slot)
+        n_done += 1
         for k in RESULT_KEYS:
             host[k].copy_(out[k], non_blocking=True)
         done = torch.cuda.Event()

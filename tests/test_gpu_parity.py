@@ -165,3 +165,26 @@ def test_match_stream_equals_direct_forward():
     for a, b in zip(direct, streamed):
         assert torch.equal(a["matches0"].cpu(), b["matches0"]) and torch.equal(a["matches1"].cpu(), b["matches1"])
         assert torch.equal(a["matching_scores0"].cpu(), b["matching_scores0"])
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_cuda_graph_mode_matches_eager(adaptive):
+    """conf.cuda_graph replays the whole forward (incl. device-side early exit / pruning) as one graph."""
+    name = "adaptive_n512" if adaptive else "c1_n512"
+    fix, data, sd = load_case(name)
+    rc, conf = fix["recipe"], fix["conf"]
+    outs = []
+    for g in (False, True):
+        m = LightGlue(features=None, input_dim=rc["d"], precision="bf16x3", cuda_graph=g, **conf)
+        m.load_state_dict(sd, strict=False)
+        m = m.eval().cuda()
+        m.pruning_keypoint_thresholds = dict(LightGlue.pruning_keypoint_thresholds, flash=rc.get("pruning_threshold", -1))
+        d = to_cuda(data)
+        o = m(d)
+        o = m(d)  # second call replays the captured graph
+        outs.append(o)
+    a, b = outs
+    assert a["stop"] == b["stop"]
+    for k in ("matches0", "matches1", "matching_scores0", "matching_scores1", "prune0", "prune1"):
+        assert torch.equal(a[k], b[k]), k
+    assert all(torch.equal(x, y) for x, y in zip(a["matches"], b["matches"]))
