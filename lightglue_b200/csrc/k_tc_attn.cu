@@ -326,6 +326,228 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
+// Variant B: same tiling (256 query rows per CTA, 64-key blocks) but only 256 TMEM columns and ~100 KB of
+// shared memory per CTA, so TWO CTAs are resident per SM: four softmax warps per scheduler instead of two
+// hide the TMEM-load / barrier latencies of a block.  S is single-buffered (S_t 64 columns, P in place),
+// O_t has 64 columns and the softmax denominator is summed in registers.
+// TMEM map (256 columns): S0 0-63 | S1 64-127 | O0 128-191 | O1 192-255.
+// ------------------------------------------------------------------------------------------------
+constexpr int B_KV_STAGES = 4;
+constexpr int B_V_TILE_BYTES = 64 * 128;                      // [64 d rows][64 keys]
+constexpr int B_STAGE_BYTES = K_TILE_BYTES + B_V_TILE_BYTES;  // 16 KB
+
+template <bool FAST>
+__global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_constant__ AttnParams p) {
+  const int s = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * 2 * QT;
+  const int len_q = p.st.len[s];
+  if (r0 >= len_q || lg_pair_stopped(p.st, s)) return;
+  const int skv = (s + p.kv_shift) % p.st.S;
+  const int len_kv = p.st.len[skv];
+  const int nkv = (len_kv + KB - 1) / KB;
+  const int nt = (len_q - r0 > QT) ? 2 : 1;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sq = smem;                                  // 2 x 16 KB
+  uint8_t* skvb = smem + 2 * Q_TILE_BYTES;             // B_KV_STAGES x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(skvb + B_KV_STAGES * B_STAGE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + B_KV_STAGES;
+  uint64_t* s_full = kv_empty + B_KV_STAGES;  // [2]
+  uint64_t* p_full = s_full + 2;              // [2]
+  uint64_t* o_final = p_full + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.q_map);
+    tma_prefetch_desc(&p.k_map);
+    tma_prefetch_desc(&p.vt_map);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < B_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], nt); }
+    for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128); mbar_init(&o_final[t], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (nkv > 0) {
+      if (warp == 0) {
+        if (elect_one()) {
+          mbar_arrive_expect_tx(q_full, 2 * Q_TILE_BYTES);
+          tma_load_3d(sq, &p.q_map, 0, r0, s * LG_HEADS + h, q_full);
+          tma_load_3d(sq + Q_TILE_BYTES, &p.q_map, 0, r0 + QT, s * LG_HEADS + h, q_full);
+          for (int j = 0; j < nkv; ++j) {
+            const int stage = j % B_KV_STAGES, round = j / B_KV_STAGES;
+            mbar_wait(&kv_empty[stage], (round & 1) ^ 1, p.dbg, 1, j);
+            uint8_t* dst = skvb + stage * B_STAGE_BYTES;
+            mbar_arrive_expect_tx(&kv_full[stage], B_STAGE_BYTES);
+            tma_load_3d(dst, &p.k_map, 0, j * KB, skv * LG_HEADS + h, &kv_full[stage]);
+            tma_load_3d(dst + K_TILE_BYTES, &p.vt_map, j * KB, 0, skv * LG_HEADS + h, &kv_full[stage]);
+          }
+        }
+      } else if (warp - 1 < nt) {
+        // MMA issuer of tile t: S_t(0); then per block: wait P_t(j) -> O_t += P_t V_j ; S_t(j+1) = Q_t K_{j+1}^T
+        const int t = warp - 1;
+        constexpr uint32_t idesc_qk = make_idesc(QT, KB, false);  // M=128 N=64, fp16
+        constexpr uint32_t idesc_pv = make_idesc(QT, 64, false);  // M=128 N=64, fp16
+        const uint64_t qdesc = make_sdesc_sw128(smem_u32(sq + t * Q_TILE_BYTES));
+        const uint64_t kdesc0 = make_sdesc_sw128(smem_u32(skvb));
+        const uint64_t vdesc0 = make_sdesc_sw128(smem_u32(skvb + K_TILE_BYTES));
+        const uint32_t ts_addr = tmem_base + t * 64;
+        const uint32_t to_addr = tmem_base + 128 + t * 64;
+        auto issue_qk = [&](int j) {
+          const uint64_t kdesc = kdesc0 + (uint64_t)((j % B_KV_STAGES) * (B_STAGE_BYTES >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ss(ts_addr, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
+          mma_commit(&s_full[t]);
+        };
+        mbar_wait(q_full, 0, p.dbg, 2);
+        mbar_wait(&kv_full[0], 0, p.dbg, 3);
+        tc_fence_after();
+        if (elect_one()) issue_qk(0);
+        __syncwarp();
+        for (int j = 0; j < nkv; ++j) {
+          const int stage = j % B_KV_STAGES;
+          if (j + 1 < nkv) mbar_wait(&kv_full[(j + 1) % B_KV_STAGES], ((j + 1) / B_KV_STAGES) & 1, p.dbg, 4, j);
+          mbar_wait(&p_full[t], j & 1, p.dbg, 5, j * 2 + t);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t vdesc = vdesc0 + (uint64_t)(stage * (B_STAGE_BYTES >> 4));
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_ts(to_addr, ts_addr + ks * 8, vdesc + 2 * ks, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+            mma_commit(&kv_empty[stage]);
+            // in-order tensor pipe: S_t(j+1) overwrites S_t / P_t(j) only after P_t(j) V_j has consumed it
+            if (j + 1 < nkv) issue_qk(j + 1);
+            else mma_commit(&o_final[t]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int t = (warp - 4) / 4;
+    const int quarter = warp % 4;
+    const int row = quarter * 32 + lane;
+    const int r = r0 + t * QT + row;
+    const long off = ((long)s * p.st.Lp + r) * LG_DIM + h * LG_HDIM;
+    if (nkv > 0) {
+      if (t < nt) {
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        const uint32_t ts = tmem_base + lane_off + t * 64;
+        const uint32_t to = tmem_base + lane_off + 128 + t * 64;
+        float m_used = -INFINITY, l = 0.f;
+        uint32_t sv[2][32];
+        for (int j = 0; j < nkv; ++j) {
+          mbar_wait(&s_full[t], j & 1, p.dbg, 6, j * 2 + t);
+          tc_fence_after();
+          const int valid = len_kv - j * KB;
+          tmem_ld32(ts, sv[0]);
+          tmem_ld32(ts + 32, sv[1]);
+          tmem_ld_wait();
+          if (valid < KB) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;
+          }
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              mx0 = max3(mx0, __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+              mx1 = max3(mx1, __uint_as_float(sv[c][i + 2]), __uint_as_float(sv[c][i + 3]));
+            }
+          const float mx = fmaxf(mx0, mx1);
+          float alpha = 1.f;
+          bool need = false;
+          if (mx > m_used) {
+            if (m_used == -INFINITY) { m_used = mx; }
+            else if ((mx - m_used) * SCALE_LOG2 > 8.f) { alpha = ex2((m_used - mx) * SCALE_LOG2); m_used = mx; need = true; }
+          }
+          if (__any_sync(0xffffffffu, need)) {  // S_t(j) was issued after P_t(j-1) V: that MMA has retired
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o16[16];
+              tmem_ld16(to + c * 16, o16);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o16[i] = __float_as_uint(__uint_as_float(o16[i]) * alpha);
+              tmem_st16(to + c * 16, o16);
+            }
+            l *= alpha;
+          }
+          const float mc = m_used * SCALE_LOG2;
+          float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float x0 = fmaf(__uint_as_float(sv[c][2 * i]), SCALE_LOG2, -mc);
+              const float x1 = fmaf(__uint_as_float(sv[c][2 * i + 1]), SCALE_LOG2, -mc);
+              const float e0 = ex2(x0), e1 = ex2(x1);
+              l0 += e0; l1 += e1;
+              const __half2 hh = __floats2half2_rn(e0, e1);
+              pk[i] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            tmem_st16(ts + c * 16, pk);
+          }
+          l += l0 + l1;
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_full[t]);
+        }
+        mbar_wait(&o_final[t], 0, p.dbg, 8, t);
+        tc_fence_after();
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld32(to + c * 32, sv[c]);
+          tmem_ld_wait();
+          if (r < len_q) {
+            uint32_t ph[16], pl[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a = __uint_as_float(sv[c][2 * i]) * inv, b = __uint_as_float(sv[c][2 * i + 1]) * inv;
+              const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+              ph[i] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+              const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha));
+              const __nv_bfloat16 lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+              pl[i] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              reinterpret_cast<uint4*>(p.ctxh + off + c * 32)[i] = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
+              if (p.ctxl)
+                reinterpret_cast<uint4*>(p.ctxl + off + c * 32)[i] = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
+            }
+          }
+        }
+      }
+    } else if (r < len_q) {
+      for (int i = 0; i < 8; ++i) {
+        reinterpret_cast<uint4*>(p.ctxh + off)[i] = make_uint4(0, 0, 0, 0);
+        if (p.ctxl) reinterpret_cast<uint4*>(p.ctxl + off)[i] = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
 // CUDA-core reference kernel on the same fp16 operands (debug comparator: LG_TC_ATTN_REF=1)
 // ------------------------------------------------------------------------------------------------
 #define AT 64
@@ -481,6 +703,23 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
   AttnParams p;
   p.q_map = c->qm; p.k_map = c->km; p.vt_map = c->vm;
   p.ctxh = b.ctxh; p.ctxl = b.ctxl; p.kv_shift = kv_shift; p.st = st; p.dbg = h->tc.dbg;
+  static const int variant = getenv("LG_TC_ATTN_V") ? atoi(getenv("LG_TC_ATTN_V")) : 2;
+  dim3 grid((st.Lp + 2 * QT - 1) / (2 * QT), LG_HEADS, st.S);
+  if (variant == 2) {
+    constexpr int smem2 = 2 * Q_TILE_BYTES + B_KV_STAGES * B_STAGE_BYTES + 1024 + 256;
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaError_t e = cudaFuncSetAttribute(tc_attention2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(tc_attention2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+      if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
+      attr2 = true;
+    }
+    if (h->cfg.precision == LG_PREC_BF16) tc_attention2_kernel<true><<<grid, 384, smem2, stream>>>(p);
+    else tc_attention2_kernel<false><<<grid, 384, smem2, stream>>>(p);
+    LG_CHECK_LAUNCH();
+    return 0;
+  }
   constexpr int smem = 2 * Q_TILE_BYTES + KV_STAGES * KV_STAGE_BYTES + 1024 + 256;
   static bool attr = false;
   if (!attr) {
@@ -490,7 +729,6 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
     if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
     attr = true;
   }
-  dim3 grid((st.Lp + 2 * QT - 1) / (2 * QT), LG_HEADS, st.S);
   if (h->cfg.precision == LG_PREC_BF16) tc_attention_kernel<true><<<grid, 384, smem, stream>>>(p);
   else tc_attention_kernel<false><<<grid, 384, smem, stream>>>(p);
   LG_CHECK_LAUNCH();
