@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");  // 80 -> 32 frees 6144 registers = exactly what 2 x 128 x (104 - 80) needs
     if (nkv > 0) {
       if (warp == 0) {
         if (elect_one()) {
