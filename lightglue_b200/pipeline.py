@@ -42,7 +42,11 @@ def match_stream(matcher, batches: Iterable[dict], device: torch.device | None =
     except StopIteration:
         return
     pending = None  # (host result dict, event) of the previous batch
-    slots = [dict(), dict(), dict()]  # ring of pinned result buffers (pinned allocation is slow: reuse)
+    # ring of pinned result buffers, kept on the matcher: pinned allocation (cudaHostAlloc) is slow, reuse it
+    slots = getattr(matcher, "_stream_slots", None)
+    if slots is None:
+        slots = [dict(), dict(), dict()]
+        matcher._stream_slots = slots
     n_done = 0
     while nxt is not None:
         dev, ev = nxt
