@@ -318,6 +318,30 @@ def main():
                         "frac": ach / peak, "traffic": None, "peak_source": how + ", sustained (kernel timed inside a long step)",
                         "flops_per_launch": attention_flops_per_launch(B), "avg_launch_ms": att_ms / att_n}
 
+    # ---- assignment kernel, materialising variant (MatchAssignment.forward's declared output, lightglue.py:296):
+    # the sweep that writes the [B, M+1, N+1] fp32 log-assignment matrix is HBM-bound (18.9 MB / pair)
+    roofline_assign = None
+    if rank == 0 and args.precision != "fp32":
+        g = torch.Generator().manual_seed(3)
+        xa = torch.randn(B, N_KPTS, 256, generator=g).to(dev)
+        xb = torch.randn(B, N_KPTS, 256, generator=g).to(dev)
+        for _ in range(2):
+            matcher.log_assignment_matrix(8, xa, xb)
+        matcher.timing = True
+        for _ in range(3):
+            matcher.log_assignment_matrix(8, xa, xb)
+        torch.cuda.synchronize(dev)
+        kt2 = matcher.kernel_times()
+        am_ms, am_n = kt2.get("assign_matrix", (0.0, 0))
+        if am_n > 0:
+            peaks, how = measured_peaks()
+            abytes = 18.9e6 * B
+            ach = abytes / ((am_ms / am_n) / 1000.0) / 1e9
+            roofline_assign = {"kernel": "assignment sweep 2 (+ log-assignment matrix write)", "bound": "hbm", "achieved": ach,
+                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                               "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": am_ms / am_n, "peak_source": how}
+        del xa, xb
+
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = pick_cpu_threads()
@@ -343,6 +367,7 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "roofline": roofline,
+            "roofline_assign": roofline_assign,
             "cpu_baseline": cpu_baseline,
             "kernel_ms": kernel_ms,
             "whole_forward": {"algorithmic_flops_per_pair": flops,

@@ -591,6 +591,13 @@ __global__ void __launch_bounds__(1024) assign_output_kernel(AssignArgs a, SeqSt
   if (tid == 0) a.n_matches[b] = carry;
 }
 
+int misc_assign_dustbin(const AssignArgs& a, const SeqState& st, cudaStream_t stream) {
+  const int mx = a.M > a.N ? a.M : a.N;
+  assign_dustbin_kernel<<<dim3((mx + 256) / 256, st.B), 256, 0, stream>>>(a, st);
+  LG_CHECK_LAUNCH();
+  return 0;
+}
+
 int misc_assign_z(const AssignArgs& a, const SeqState& st, cudaStream_t stream) {
   assign_z_kernel<<<dim3(st.Lp / 8, st.S), 256, 0, stream>>>(a, st);
   LG_CHECK_LAUNCH();

@@ -38,6 +38,7 @@ struct TcLinParams {
                                  // 2: third TMA coordinate = partner sequence (similarity sweeps of the assignment)
   float* part; int* part_arg; int part_stride;  // TEPI_LSE: (max, sumexp) pairs; TEPI_ARGMAX: best / arg, [S*Lp, part_stride]
   const float* term;             // TEPI_ARGMAX: logsigmoid(z) - LSE per token, [S, Lp]
+  float* logmat; int mat_m, mat_n;  // TEPI_ARGMAX, optional: materialise the [B, M+1, N+1] log-assignment matrix (core block)
   const float* bias; long bias_sel_stride;
   float scale;
   float* out_f32; int ldo;
@@ -291,6 +292,9 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
         } else {
           // score = 2 S + term_s[i] + term_partner[j]; the row term does not move the arg-max
           const float* ct = p.term + (long)ti.sel * p.st.Lp + ti.n_tile * BN + half * HCOLS;
+          const float rterm = live ? p.term[grow] : 0.f;
+          // the matrix is written from the image0 side only (rows = image0 points, columns = image1 points)
+          const bool write_mat = NSLOT == 1 && p.logmat != nullptr && ti.s < p.st.B;
           float best = -INFINITY; int arg = 0;
           for (int c0 = 0; c0 < HCOLS && c0 < ncols; c0 += 32) {
             tmem_ld32(tl + c0, raw);
@@ -304,11 +308,30 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
                 const int j = j4 * 4 + jj;
                 const float sc = fmaf(2.f, __uint_as_float(raw[j]), cc[jj]);
                 if (c0 + j < ncols && sc > best) { best = sc; arg = ti.n_tile * BN + half * HCOLS + c0 + j; }  // first max wins
+                raw[j] = __float_as_uint(sc + rterm);
+              }
+            }
+            if (write_mat) {
+              // stage the 32 x 32 block (swizzled), then every row leaves as one 128-byte store of the warp:
+              // the (N+1)-float row pitch of the reference's matrix is only 4-byte aligned, so no TMA here
+              __syncwarp();
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                *reinterpret_cast<uint4*>(arow + ((j4 ^ sw) << 4)) = make_uint4(raw[4 * j4], raw[4 * j4 + 1], raw[4 * j4 + 2], raw[4 * j4 + 3]);
+              __syncwarp();
+              const int cj = ti.n_tile * BN + half * HCOLS + c0 + lane;   // this lane's column
+              const int rbase = ti.r0 + quarter * 32;
+              float* mo = p.logmat + ((long)ti.s * (p.mat_m + 1) + rbase) * (p.mat_n + 1) + cj;
+              const bool col_ok = c0 + lane < ncols;
+#pragma unroll 8
+              for (int rr = 0; rr < 32; ++rr) {
+                const float val = *reinterpret_cast<const float*>(boxA + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2)));
+                if (col_ok && rbase + rr < ti.len) mo[(long)rr * (p.mat_n + 1)] = val;
               }
             }
           }
           if (live) {
-            p.part[grow * p.part_stride + slot] = best + p.term[grow];
+            p.part[grow * p.part_stride + slot] = best + rterm;
             p.part_arg[grow * p.part_stride + slot] = arg;
           }
         }
@@ -755,13 +778,15 @@ __global__ void assign_best_combine_kernel(const float* __restrict__ part, const
 }  // namespace
 
 int tc_assign_sweeps(LgHandle* h, const TcBuffers& b, const SeqState& st, const float* z, float* part, int* part_arg,
-                     float* term, float* rowbest, int* rowarg, float* colbest, int* colarg, int nt64, cudaStream_t stream) {
+                     float* term, float* rowbest, int* rowarg, float* colbest, int* colarg, int nt64, float* logmat, int M, int N,
+                     cudaStream_t stream) {
   const int ntc = (st.Lp + BN - 1) / BN;
   for (int sweep = 0; sweep < 2; ++sweep) {
     TcLinParams p{};
     p.epi = sweep == 0 ? TEPI_LSE : TEPI_ARGMAX;
     p.scale = 1.f; p.bias = h->wpk;  // unused
     p.part = part; p.part_arg = part_arg; p.part_stride = 2 * ntc; p.term = term;
+    p.logmat = sweep == 1 ? logmat : nullptr; p.mat_m = M; p.mat_n = N;
     p.w_select = 2;
     const bool x3 = h->cfg.precision == LG_PREC_BF16X3;
     const uint64_t rows = (uint64_t)st.S * st.Lp;
@@ -775,7 +800,10 @@ int tc_assign_sweeps(LgHandle* h, const TcBuffers& b, const SeqState& st, const 
     p.kb0 = LG_DIM / BK; p.kb_total = LG_DIM / BK; p.passes = x3 ? 3 : 1;
     p.st = st; p.dbg = h->tc.dbg;
     h->launches += 1;
-    if ((r = launch_linear(p, ntc, stream))) return r;
+    {
+      Timer tm(h, sweep == 1 && logmat ? LG_K_ASSIGN_MATRIX : LG_K_ASSIGN, stream);
+      if ((r = launch_linear(p, ntc, stream))) return r;
+    }
     if (sweep == 0) {
       assign_lse_combine_kernel<<<dim3((st.Lp + 255) / 256, st.S), 256, 0, stream>>>(part, z, term, 2 * ntc, st);
       LG_CHECK_LAUNCH();

@@ -123,6 +123,7 @@ struct AssignArgs {
 };
 int misc_assign(const AssignArgs& a, const SeqState& st, cudaStream_t stream, int64_t* launches);
 int misc_assign_z(const AssignArgs& a, const SeqState& st, cudaStream_t stream);
+int misc_assign_dustbin(const AssignArgs& a, const SeqState& st, cudaStream_t stream);
 int misc_assign_tail(const AssignArgs& a, const SeqState& st, cudaStream_t stream, int64_t* launches);
 int misc_export_stop_prune(const int* stop_layer, const int* prune, int* stop_out, int* prune0, int* prune1, int B, int M,
                            int N, int Lp, cudaStream_t stream);

@@ -397,6 +397,9 @@ class LightGlue(nn.Module):
                 m0.data_ptr(), m1.data_ptr(), ms0.data_ptr(), ms1.data_ptr(), meta[0].data_ptr(), None, None,
                 meta[1].data_ptr(), pairs.data_ptr(), pscores.data_ptr(), full.data_ptr(),
             )
+            if self.timing:
+                lib.lg_timing_enable(handle, 1)
+                self.timing = False
             stream = torch.cuda.current_stream(device).cuda_stream
             _cabi.check(
                 lib.lg_assign(handle, layer, b, m, n, x0.data_ptr(), x1.data_ptr(), C.byref(out), ws.data_ptr(),
@@ -411,7 +414,7 @@ class LightGlue(nn.Module):
             return {}
         lib = _cabi.load()
         res = {}
-        for name, kc in (("attention", 0), ("linear", 1), ("assign", 2), ("other", 3)):
+        for name, kc in (("attention", 0), ("linear", 1), ("assign", 2), ("other", 3), ("assign_matrix", 4)):
             ms, cnt = C.c_double(), C.c_int64()
             _cabi.check(lib.lg_kernel_time_ms(self._handle[0], kc, C.byref(ms), C.byref(cnt)), "lg_kernel_time_ms")
             res[name] = (ms.value, cnt.value)

@@ -188,3 +188,21 @@ def test_cuda_graph_mode_matches_eager(adaptive):
     for k in ("matches0", "matches1", "matching_scores0", "matching_scores1", "prune0", "prune1"):
         assert torch.equal(a[k], b[k]), k
     assert all(torch.equal(x, y) for x, y in zip(a["matches"], b["matches"]))
+
+
+def test_log_assignment_matrix_tensor_core_variant():
+    """The materialising assignment variant on the tensor-core sweep (bf16x3): matrix within 2e-3 of the
+    oracle's, identical filter_matches indices."""
+    torch.manual_seed(6)
+    sd = synth.make_state_dict()
+    m = LightGlue(features=None, precision="bf16x3", depth_confidence=-1, width_confidence=-1)
+    m.load_state_dict(sd, strict=False)
+    m = m.cuda()
+    x0 = torch.randn(2, 300, 256)
+    x1 = torch.randn(2, 517, 256)
+    full, m0, m1, ms0, ms1 = m.log_assignment_matrix(3, x0.cuda(), x1.cuda())
+    ref = oracle.log_assignment(sd, 3, x0, x1)
+    assert float((full.cpu() - ref).abs().max()) < 2e-3
+    r0, r1, rs0, rs1 = oracle.filter_matches(ref, 0.1)
+    assert torch.equal(m0.cpu(), r0) and torch.equal(m1.cpu(), r1)
+    assert float((ms0.cpu() - rs0).abs().max()) < 1e-3
