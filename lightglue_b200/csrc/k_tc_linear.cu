@@ -801,7 +801,7 @@ int tc_assign_sweeps(LgHandle* h, const TcBuffers& b, const SeqState& st, const 
     p.st = st; p.dbg = h->tc.dbg;
     h->launches += 1;
     {
-      Timer tm(h, sweep == 1 && logmat ? LG_K_ASSIGN_MATRIX : LG_K_ASSIGN, stream);
+      Timer tm(h, LG_K_ASSIGN_MATRIX, stream, sweep == 1 && logmat != nullptr);  // the matrix-writing sweep on its own
       if ((r = launch_linear(p, ntc, stream))) return r;
     }
     if (sweep == 0) {

@@ -48,7 +48,8 @@ struct LgHandle {
 // per-kernel-class device times).  No-op unless lg_timing_enable(h, 1).
 struct Timer {
   LgHandle* h; int kc; cudaStream_t s; bool on;
-  Timer(LgHandle* h_, int kc_, cudaStream_t s_) : h(h_), kc(kc_), s(s_), on(h_->timing) {
+  // Timers of the SAME class must not nest (they share one cursor); `enable` = false makes this one inert.
+  Timer(LgHandle* h_, int kc_, cudaStream_t s_, bool enable = true) : h(h_), kc(kc_), s(s_), on(h_->timing && enable) {
     if (!on) return;
     if (h->ev_used[kc] + 2 > 40000) { on = false; return; }
     while (h->ev[kc].size() < h->ev_used[kc] + 2) {
