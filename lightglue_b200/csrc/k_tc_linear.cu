@@ -49,6 +49,7 @@ struct TcLinParams {
   // epilogue tensor maps (all boxes are 32 rows x 128 bytes, 128B swizzle)
   CUtensorMap o_h;          // bf16 hi output [rows, ldb], box 64 cols x 32 rows, 128B swizzle (two chunks per store)
   CUtensorMap o_l32;        // bf16 lo output, box 32 cols x 32 rows, no swizzle (one chunk per store)
+  CUtensorMap o_h32;        // bf16 hi output, same dense box (LayerNorm variant)
   CUtensorMap o_f32;        // fp32 output / residual [rows, 256], box 32 cols (TEPI_RESID loads and stores through it)
   CUtensorMap o_q, o_k;     // fp16 [S*H, Lp, 64], box (64, 32, 1)
   CUtensorMap cs_map;       // fp32 [rows, 64] cos | sin, box 32 cols
@@ -63,23 +64,27 @@ struct TcLinParams {
 // shared memory (XOR-swizzled, conflict-free both ways) -> registers in a row-contiguous layout (8 lanes
 // x 16 B per row) -> coalesced global loads / stores.
 // ------------------------------------------------------------------------------------------------
-constexpr int EPI_WARPS = 8;
-constexpr int LIN_THREADS = 64 + EPI_WARPS * 32;
 
 template <int NSLOT>
 struct LinCfg {
   static constexpr int STAGES = 2;
   static constexpr int NBUF = NSLOT == 1 ? 2 : 1;
+  // epilogue warps: 8 (two per TMEM lane quarter, 128 columns each); the LayerNorm variant (512 columns, the
+  // instruction-heaviest epilogue) runs 16 so that four warps per scheduler hide its latencies
+  static constexpr int EW = NSLOT == 1 ? 8 : 16;
+  static constexpr int GROUPS = EW / 4;
+  static constexpr int THREADS = 64 + EW * 32;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + NSLOT * W_TILE_BYTES;
   static constexpr int COLS = NSLOT * BN;
   // per epilogue warp: box A (4 KB: fp32 32x32 output box / rotary cos), box B (4 KB: 16-bit 32x64 box, hi or
   // fp16), box C (4 KB: rotary sin, or the dense 32x32 bf16 "lo" box).  The LayerNorm variant has no box A.
-  static constexpr int WARP_BYTES = NSLOT == 1 ? 3 * 4096 : 4096 + 2048;
+  // (NSLOT == 2: one dense 32x32 bf16 box, 2 KB, shared by the hi and lo images)
+  static constexpr int WARP_BYTES = NSLOT == 1 ? 3 * 4096 : 2048;
   static constexpr int BOXB_OFF = NSLOT == 1 ? 4096 : 0;
-  static constexpr int BOXC_OFF = NSLOT == 1 ? 8192 : 4096;
+  static constexpr int BOXC_OFF = NSLOT == 1 ? 8192 : 0;
   static constexpr int VEC_BYTES = 3 * COLS * 4;            // bias | ln gamma | ln beta
-  static constexpr int LNP_BYTES = 128 * 2 * 8;             // LayerNorm partial (mean, M2) per row per column half
-  static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_WARPS * WARP_BYTES + VEC_BYTES + LNP_BYTES + 512 + 1024;
+  static constexpr int LNP_BYTES = 128 * GROUPS * 8;        // LayerNorm partial (mean, M2) per row per column group
+  static constexpr int SMEM = STAGES * STAGE_BYTES + EW * WARP_BYTES + VEC_BYTES + LNP_BYTES + 512 + 1024;
 };
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -92,7 +97,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps
+template <int NTHREADS>
+__device__ __forceinline__ void epi_bar_n() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }  // the epilogue warps
 
 struct TileInfo {
   int s, r0, n_tile, sel, len;
@@ -120,8 +126,10 @@ __device__ __forceinline__ bool decode_tile(const TcLinParams& p, int t, int n_t
 }
 
 template <int NSLOT, int EPI>
-__global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_constant__ TcLinParams p) {
+__global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(const __grid_constant__ TcLinParams p) {
   using C = LinCfg<NSLOT>;
+  constexpr int EPI_WARPS = C::EW;
+  auto epi_bar = [] { epi_bar_n<C::EW * 32>(); };
   constexpr int STAGES = C::STAGES, NBUF = C::NBUF, STAGE_BYTES = C::STAGE_BYTES, COLS = C::COLS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
   float* s_bias = reinterpret_cast<float*>(epi_smem + EPI_WARPS * C::WARP_BYTES);
   float* s_gamma = s_bias + COLS;
   float* s_beta = s_gamma + COLS;
-  float2* s_lnp = reinterpret_cast<float2*>(s_beta + COLS);  // [2 halves][128 rows]
+  float2* s_lnp = reinterpret_cast<float2*>(s_beta + COLS);  // [GROUPS][128 rows]
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_lnp) + C::LNP_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
@@ -224,9 +232,9 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
     // residual and the rotary tables arrive the same way through TMA loads.  No per-lane global traffic.
     const int ew = warp - 2;
     const int quarter = warp % 4;                 // TMEM lane group this warp may read
-    const int half = ew / 4;                      // which half of the tile's columns this warp owns
-    constexpr int HCOLS = COLS / 2;               // columns per warp
-    const int te = threadIdx.x - 64;              // 0..255
+    const int half = ew / 4;                      // which column group of the tile this warp owns
+    constexpr int HCOLS = COLS / C::GROUPS;       // columns per warp (128)
+    const int te = threadIdx.x - 64;              // index among the epilogue threads
     uint8_t* wsm = epi_smem + ew * C::WARP_BYTES;
     uint8_t* boxA = wsm;                          // fp32 box / cos (NSLOT == 1 only)
     uint8_t* boxB = wsm + C::BOXB_OFF;            // 16-bit box: 32 rows x 64 elements, swizzled
@@ -356,15 +364,19 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
               s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
             }
           }
-          // this half: mean_h = sh + s1/H, M2_h = sum (v - mean_h)^2 = s2 - s1^2/H (shifted -> no cancellation);
-          // halves merge with Chan's formula: M2 = M2_a + M2_b + (mean_a - mean_b)^2 * H / 2
+          // this group: mean_g = sh + s1/H, M2_g = sum (v - mean_g)^2 = s2 - s1^2/H (shifted -> no cancellation);
+          // equal-sized groups merge with Chan's formula: mean = avg(mean_g), M2 = sum M2_g + H * sum (mean_g - mean)^2
           const float mh = sh + s1 * (1.f / HCOLS);
           s_lnp[half * 128 + row] = make_float2(mh, s2 - s1 * s1 * (1.f / HCOLS));
           epi_bar();
-          const float2 a = s_lnp[row], b = s_lnp[128 + row];
-          mean = 0.5f * (a.x + b.x);
-          const float dm = a.x - b.x;
-          const float var = fmaxf((a.y + b.y + dm * dm * (0.5f * HCOLS)) * (1.f / COLS), 0.f);
+          float msum = 0.f, m2 = 0.f;
+#pragma unroll
+          for (int g = 0; g < C::GROUPS; ++g) { const float2 a = s_lnp[g * 128 + row]; msum += a.x; m2 += a.y; }
+          mean = msum * (1.f / C::GROUPS);
+          float dev = 0.f;
+#pragma unroll
+          for (int g = 0; g < C::GROUPS; ++g) { const float dm = s_lnp[g * 128 + row].x - mean; dev = fmaf(dm, dm, dev); }
+          const float var = fmaxf((m2 + dev * HCOLS) * (1.f / COLS), 0.f);
           rstd = rsqrtf(var + 1e-5f);
         }
         for (int c0 = 0; c0 < HCOLS; c0 += 32) {
@@ -457,6 +469,40 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) tc_linear_kernel(const __grid_
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4)
               *reinterpret_cast<float4*>(arow + ((j4 ^ sw) << 4)) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          }
+          if (NSLOT == 2) {
+            // LayerNorm variant: one dense 32 x 32 bf16 box per warp; hi leaves first, then (bf16x3) lo through the same box
+            for (int pass = 0; pass < (haslo ? 2 : 1); ++pass) {
+              if (pass == 1) {
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+              }
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a = v[8 * j8 + 2 * e], b = v[8 * j8 + 2 * e + 1];
+                  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+                  if (pass == 0) {
+                    w[e] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+                  } else {
+                    const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha));
+                    const __nv_bfloat16 lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+                    w[e] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+                  }
+                }
+                *reinterpret_cast<uint4*>(crow_lo + (j8 << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(pass == 0 ? &p.o_h32 : &p.o_l32, boxC, col, grow_w);
+                tma_store_commit();
+              }
+            }
+            __syncwarp();
+            continue;
           }
           if (has16) {
 #pragma unroll
@@ -676,7 +722,7 @@ int launch_linear_t(TcLinParams& p, int n_tiles, cudaStream_t stream) {
   p.n_tiles = n_tiles;
   const int total = n_tiles * p.st.S * (p.st.Lp / BM);
   const int grid = total < g_num_sms ? total : g_num_sms;
-  tc_linear_kernel<NSLOT, EPI><<<grid, LIN_THREADS, smem, stream>>>(p);
+  tc_linear_kernel<NSLOT, EPI><<<grid, LinCfg<NSLOT>::THREADS, smem, stream>>>(p);
   LG_CHECK_LAUNCH();
   return 0;
 }
@@ -719,6 +765,7 @@ int run_linear(LgHandle* h, const SeqState& st, const LinDesc& d, TcLinParams& p
   if (x3 && (r = wmap(h, &p.w_lo, h->tc.w_lo + d.w_off, d.nout, K, d.nsel, d.sel_stride))) return r;
   if (p.out_h && (r = omap2d(h, &p.o_h, p.out_h, 2, p.ldb, rows, 64, true))) return r;
   if (p.out_l && (r = omap2d(h, &p.o_l32, p.out_l, 2, p.ldb, rows, 32, false))) return r;
+  if (p.out_h && p.epi == TEPI_LN_GELU && (r = omap2d(h, &p.o_h32, p.out_h, 2, p.ldb, rows, 32, false))) return r;
   if ((p.epi == TEPI_RESID || p.epi == TEPI_F32) && (r = omap2d(h, &p.o_f32, p.out_f32, 4, p.ldo, rows, 32, true))) return r;
   if (p.epi == TEPI_QKV) {
     if ((r = omap_qk(h, &p.o_q, p.q, st.Lp, (uint64_t)st.S * LG_HEADS))) return r;
