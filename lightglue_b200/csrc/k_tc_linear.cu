@@ -13,6 +13,8 @@
 //   bias + residual for ffn.3, bias * scale for input_proj / final_proj.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue
 // (warp w reads TMEM lanes 32*(w%4) .. +31, one accumulator row per thread).
+#include <stdlib.h>
+
 #include <unordered_map>
 
 #include "lg_handle.h"
@@ -30,7 +32,8 @@ enum { TEPI_QKV = 0, TEPI_BF16 = 1, TEPI_LN_GELU = 2, TEPI_RESID = 3, TEPI_F32 =
 
 struct TcLinParams {
   CUtensorMap a_hi[2], a_lo[2];  // A segment 0 / 1
-  CUtensorMap w_hi, w_lo;        // 3-D: (K, Nout, select)
+  CUtensorMap w_hi, w_lo;        // 3-D: (K, Nout, select), box 64 x 256 rows
+  CUtensorMap w_hi_half, w_lo_half;  // same tensors, box 64 x 128 rows: each CTA of a pair loads one half and multicasts it
   int kb0, kb_total, passes, n_tiles;
   int epi, rope;
   SeqState st;
@@ -104,7 +107,7 @@ struct TileInfo {
   int s, r0, n_tile, sel, len;
   long grow0;
 };
-// decode tile t (n-tile fastest); returns false for tiles with nothing to do
+// decode tile t (n-tile fastest); returns false for tiles with nothing to do (all fields are filled either way)
 __device__ __forceinline__ bool decode_tile(const TcLinParams& p, int t, int n_tiles, TileInfo& ti) {
   const int tiles_per_seq = p.st.Lp / BM;
   ti.n_tile = t % n_tiles;
@@ -112,20 +115,58 @@ __device__ __forceinline__ bool decode_tile(const TcLinParams& p, int t, int n_t
   ti.s = rt / tiles_per_seq;
   ti.r0 = (rt % tiles_per_seq) * BM;
   ti.len = p.st.len[ti.s];
-  if (ti.r0 >= ti.len) return false;
+  ti.grow0 = (long)ti.s * p.st.Lp + ti.r0;
+  ti.sel = 0;
   const int pair = ti.s >= p.st.B ? ti.s - p.st.B : ti.s;
   const int sl = p.st.stop_layer[pair];
-  ti.sel = 0;
-  if (p.w_select == 1) ti.sel = sl - 1;
+  bool live = ti.r0 < ti.len;
+  if (p.w_select == 1) ti.sel = sl > 0 ? sl - 1 : 0;
   else if (p.w_select == 2) {
     ti.sel = ti.s >= p.st.B ? ti.s - p.st.B : ti.s + p.st.B;
-    if (ti.n_tile * BN >= p.st.len[ti.sel]) return false;  // no live columns
-  } else if (sl != 0) return false;                        // pair already exited (lightglue.py:549-550)
-  ti.grow0 = (long)ti.s * p.st.Lp + ti.r0;
-  return true;
+    live = live && ti.n_tile * BN < p.st.len[ti.sel];  // no live columns otherwise
+  } else if (sl != 0) live = false;                      // pair already exited (lightglue.py:549-550)
+  return live;
 }
 
-template <int NSLOT, int EPI>
+// Tile schedule.  Plain mode: CTA c walks tiles c, c + grid, ...  Cluster mode (MC): the two CTAs of a cluster
+// take the two row tiles of a "tile pair" with the same n-tile, so that they consume the same W tiles and each
+// loads half of every W tile, multicast to both (halves the L2 -> SM weight traffic, which bounds these GEMMs).
+template <bool MC>
+struct TileWalk {
+  int cur, step, end, rank, n_tiles;
+  __device__ TileWalk(int total_tiles, int n_tiles_) : n_tiles(n_tiles_) {
+    if (MC) {
+      rank = (int)cluster_ctarank();
+      cur = blockIdx.x / 2; step = gridDim.x / 2; end = total_tiles / 2;  // tile pairs (row tiles come in pairs: S is even)
+    } else {
+      rank = 0; cur = blockIdx.x; step = gridDim.x; end = total_tiles;
+    }
+  }
+  // returns false when done; `mine` = this CTA's tile (decoded), `run` = the CTA must run loads + MMAs,
+  // `store` = its epilogue may write
+  __device__ bool next(const TcLinParams& p, TileInfo& mine, bool& store) {
+    while (cur < end) {
+      const int id = cur;
+      cur += step;
+      if (MC) {
+        const int n_tile = id % n_tiles, rtp = id / n_tiles;
+        TileInfo peer;
+        const bool lm = decode_tile(p, (rtp * 2 + rank) * n_tiles + n_tile, n_tiles, mine);
+        const bool lp = decode_tile(p, (rtp * 2 + (rank ^ 1)) * n_tiles + n_tile, n_tiles, peer);
+        if (!lm && !lp) continue;
+        store = lm;
+        return true;
+      } else {
+        if (!decode_tile(p, id, n_tiles, mine)) continue;
+        store = true;
+        return true;
+      }
+    }
+    return false;
+  }
+};
+
+template <int NSLOT, int EPI, bool MC>
 __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(const __grid_constant__ TcLinParams p) {
   using C = LinCfg<NSLOT>;
   constexpr int EPI_WARPS = C::EW;
@@ -153,7 +194,7 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_hi[0]);
     tma_prefetch_desc(&p.w_hi);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], MC ? 2 : 1); }
     for (int i = 0; i < NBUF; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
     for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&ldbar[i], 1);
     fence_barrier_init();
@@ -164,6 +205,7 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer's barriers are initialised before anything can arrive on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -171,9 +213,10 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int g = 0;  // global k-block counter across tiles (ring position)
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        TileInfo ti;
-        if (!decode_tile(p, t, n_tiles, ti)) continue;
+      TileWalk<MC> walk(total_tiles, n_tiles);
+      TileInfo ti;
+      bool store;
+      while (walk.next(p, ti, store)) {
         for (int it = 0; it < iters; ++it, ++g) {
           const int stage = g % STAGES, round = g / STAGES;
           mbar_wait(&empty[stage], (round & 1) ^ 1, p.dbg, 17, it);
@@ -187,9 +230,15 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           tma_load_2d(sa, a_lo ? &p.a_lo[seg] : &p.a_hi[seg], kc, (int)ti.grow0, &full[stage]);
 #pragma unroll
-          for (int sl_ = 0; sl_ < NSLOT; ++sl_)
-            tma_load_3d(sa + A_TILE_BYTES + sl_ * W_TILE_BYTES, w_lo ? &p.w_lo : &p.w_hi, kb * BK,
-                        (ti.n_tile * NSLOT + sl_) * BN, ti.sel, &full[stage]);
+          for (int sl_ = 0; sl_ < NSLOT; ++sl_) {
+            if (MC)  // this CTA's half (128 rows) of the W tile, delivered to both CTAs of the pair
+              tma_load_3d_mc(sa + A_TILE_BYTES + sl_ * W_TILE_BYTES + walk.rank * (W_TILE_BYTES / 2),
+                             w_lo ? &p.w_lo_half : &p.w_hi_half, kb * BK, (ti.n_tile * NSLOT + sl_) * BN + walk.rank * (BN / 2),
+                             0, &full[stage], (uint16_t)3);
+            else
+              tma_load_3d(sa + A_TILE_BYTES + sl_ * W_TILE_BYTES, w_lo ? &p.w_lo : &p.w_hi, kb * BK,
+                          (ti.n_tile * NSLOT + sl_) * BN, ti.sel, &full[stage]);
+          }
         }
       }
     }
@@ -197,9 +246,10 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc(BM, BN, true);
     int g = 0, li = 0;  // li: index among this CTA's live tiles
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      TileInfo ti;
-      if (!decode_tile(p, t, n_tiles, ti)) continue;
+    TileWalk<MC> walk(total_tiles, n_tiles);
+    TileInfo ti;
+    bool store;
+    while (walk.next(p, ti, store)) {
       const int buf = li % NBUF;
       mbar_wait(&acc_empty[buf], ((li / NBUF) & 1) ^ 1, p.dbg, 20, li);  // epilogue has drained this accumulator
       tc_fence_after();
@@ -218,7 +268,8 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
             for (int k = 0; k < BK / 16; ++k)
               mma_ss(acc + sl_ * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          mma_commit(&empty[stage]);
+          if (MC) mma_commit_mc(&empty[stage], (uint16_t)3);  // the stage is shared: both CTAs must have consumed it
+          else mma_commit(&empty[stage]);
           if (it == iters - 1) mma_commit(&acc_full[buf]);
         }
         __syncwarp();
@@ -247,10 +298,20 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
     uint8_t* crow_lo = boxC + lane * 64;          // as a dense 64-byte row (lo)
     uint32_t ld_phase = 0;
     int li = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      TileInfo ti;
-      if (!decode_tile(p, t, n_tiles, ti)) continue;
+    TileWalk<MC> walk(total_tiles, n_tiles);
+    TileInfo ti;
+    bool store;
+    while (walk.next(p, ti, store)) {
       const int buf = li % NBUF;
+      if (!store) {  // dead tile of a live pair (only in cluster mode): drain the accumulator, write nothing
+        mbar_wait(&acc_full[buf], (li / NBUF) & 1, p.dbg, 23, li);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        ++li;
+        continue;
+      }
       const float* bias = p.bias + (p.w_select == 1 ? (long)ti.sel * p.bias_sel_stride : 0) + ti.n_tile * COLS;
       const int grow_w = (int)ti.grow0 + quarter * 32;   // first global row of this warp
       const bool is_sweep = EPI == TEPI_LSE || EPI == TEPI_ARGMAX;
@@ -553,6 +614,7 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
@@ -665,13 +727,14 @@ int amap(LgHandle* h, CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 // W operand: nsel x [Nout, K] bf16, box 64 x 256 x 1
-int wmap(LgHandle* h, CUtensorMap* out, const void* base, uint64_t Nout, uint64_t K, uint64_t nsel, uint64_t sel_stride_elems) {
+int wmap(LgHandle* h, CUtensorMap* out, const void* base, uint64_t Nout, uint64_t K, uint64_t nsel, uint64_t sel_stride_elems,
+         uint32_t box_rows = BN) {
   MapCache* mc = static_cast<MapCache*>(h->tc.map_cache);
-  MapKey key{base, Nout, K, nsel, sel_stride_elems + 2};
+  MapKey key{base, Nout, K, nsel | ((uint64_t)box_rows << 32), sel_stride_elems + 2};
   auto it = mc->m.find(key);
   if (it != mc->m.end()) { *out = it->second; return 0; }
   if (mc->m.size() > 4096) mc->m.clear();
-  int r = tc_make_tmap_3d(out, base, 2, K, Nout, nsel, K * 2, (nsel > 1 ? sel_stride_elems : Nout * K) * 2, BK, BN, 1);
+  int r = tc_make_tmap_3d(out, base, 2, K, Nout, nsel, K * 2, (nsel > 1 ? sel_stride_elems : Nout * K) * 2, BK, box_rows, 1);
   if (r) return r;
   mc->m.emplace(key, *out);
   return 0;
@@ -704,12 +767,12 @@ int omap_qk(LgHandle* h, CUtensorMap* out, const void* base, uint64_t Lp, uint64
 }
 
 int g_num_sms = 0;
-template <int NSLOT, int EPI>
+template <int NSLOT, int EPI, bool MC>
 int launch_linear_t(TcLinParams& p, int n_tiles, cudaStream_t stream) {
   constexpr int smem = LinCfg<NSLOT>::SMEM;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<NSLOT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<NSLOT, EPI, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
     if (g_num_sms <= 0) {
       int dev = 0;
@@ -721,20 +784,31 @@ int launch_linear_t(TcLinParams& p, int n_tiles, cudaStream_t stream) {
   }
   p.n_tiles = n_tiles;
   const int total = n_tiles * p.st.S * (p.st.Lp / BM);
-  const int grid = total < g_num_sms ? total : g_num_sms;
-  tc_linear_kernel<NSLOT, EPI><<<grid, LinCfg<NSLOT>::THREADS, smem, stream>>>(p);
-  LG_CHECK_LAUNCH();
+  int grid = total < g_num_sms ? total : g_num_sms;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute at[1];
+  if (MC) {
+    grid &= ~1;  // whole clusters of two (total is even: S is even)
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+  }
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(LinCfg<NSLOT>::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_linear_kernel<NSLOT, EPI, MC>, p);
+  if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
   return 0;
 }
 int launch_linear(TcLinParams& p, int n_tiles, cudaStream_t stream) {
+  static const bool use_mc = !(getenv("LG_TC_NO_MULTICAST") && atoi(getenv("LG_TC_NO_MULTICAST")) != 0);
+  const bool mc = use_mc && p.w_select == 0;  // per-tile W selection (final_proj heads, assignment sweeps) cannot share W
   switch (p.epi) {
-    case TEPI_QKV: return launch_linear_t<1, TEPI_QKV>(p, n_tiles, stream);
-    case TEPI_BF16: return launch_linear_t<1, TEPI_BF16>(p, n_tiles, stream);
-    case TEPI_LN_GELU: return launch_linear_t<2, TEPI_LN_GELU>(p, 1, stream);
-    case TEPI_RESID: return launch_linear_t<1, TEPI_RESID>(p, n_tiles, stream);
-    case TEPI_F32: return launch_linear_t<1, TEPI_F32>(p, n_tiles, stream);
-    case TEPI_LSE: return launch_linear_t<1, TEPI_LSE>(p, n_tiles, stream);
-    case TEPI_ARGMAX: return launch_linear_t<1, TEPI_ARGMAX>(p, n_tiles, stream);
+    case TEPI_QKV: return mc ? launch_linear_t<1, TEPI_QKV, true>(p, n_tiles, stream) : launch_linear_t<1, TEPI_QKV, false>(p, n_tiles, stream);
+    case TEPI_BF16: return mc ? launch_linear_t<1, TEPI_BF16, true>(p, n_tiles, stream) : launch_linear_t<1, TEPI_BF16, false>(p, n_tiles, stream);
+    case TEPI_LN_GELU: return mc ? launch_linear_t<2, TEPI_LN_GELU, true>(p, 1, stream) : launch_linear_t<2, TEPI_LN_GELU, false>(p, 1, stream);
+    case TEPI_RESID: return mc ? launch_linear_t<1, TEPI_RESID, true>(p, n_tiles, stream) : launch_linear_t<1, TEPI_RESID, false>(p, n_tiles, stream);
+    case TEPI_F32: return mc ? launch_linear_t<1, TEPI_F32, true>(p, n_tiles, stream) : launch_linear_t<1, TEPI_F32, false>(p, n_tiles, stream);
+    case TEPI_LSE: return launch_linear_t<1, TEPI_LSE, false>(p, n_tiles, stream);
+    case TEPI_ARGMAX: return launch_linear_t<1, TEPI_ARGMAX, false>(p, n_tiles, stream);
   }
   return lg_set_error("launch_linear: bad epilogue");
 }
@@ -763,6 +837,11 @@ int run_linear(LgHandle* h, const SeqState& st, const LinDesc& d, TcLinParams& p
   if ((r = wmap(h, &p.w_hi, h->tc.w_hi + d.w_off, d.nout, K, d.nsel, d.sel_stride))) return r;
   p.w_lo = p.w_hi;
   if (x3 && (r = wmap(h, &p.w_lo, h->tc.w_lo + d.w_off, d.nout, K, d.nsel, d.sel_stride))) return r;
+  if (d.nsel == 1) {  // half-height boxes for the multicast path
+    if ((r = wmap(h, &p.w_hi_half, h->tc.w_hi + d.w_off, d.nout, K, 1, 0, BN / 2))) return r;
+    p.w_lo_half = p.w_hi_half;
+    if (x3 && (r = wmap(h, &p.w_lo_half, h->tc.w_lo + d.w_off, d.nout, K, 1, 0, BN / 2))) return r;
+  }
   if (p.out_h && (r = omap2d(h, &p.o_h, p.out_h, 2, p.ldb, rows, 64, true))) return r;
   if (p.out_l && (r = omap2d(h, &p.o_l32, p.out_l, 2, p.ldb, rows, 32, false))) return r;
   if (p.out_h && p.epi == TEPI_LN_GELU && (r = omap2d(h, &p.o_h32, p.out_h, 2, p.ldb, rows, 32, false))) return r;
