@@ -297,11 +297,8 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float a = __uint_as_float(sv[c][2 * i]) * inv, b = __uint_as_float(sv[c][2 * i + 1]) * inv;
-              const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-              ph[i] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
-              const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha));
-              const __nv_bfloat16 lb = __float2bfloat16_rn(b - __bfloat162float(hb));
-              pl[i] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+              ph[i] = pack_bf16x2(a, b);
+              pl[i] = pack_bf16x2_lo(a, b, ph[i]);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -520,11 +517,8 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float a = __uint_as_float(sv[c][2 * i]) * inv, b = __uint_as_float(sv[c][2 * i + 1]) * inv;
-              const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-              ph[i] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
-              const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha));
-              const __nv_bfloat16 lb = __float2bfloat16_rn(b - __bfloat162float(hb));
-              pl[i] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+              ph[i] = pack_bf16x2(a, b);
+              pl[i] = pack_bf16x2_lo(a, b, ph[i]);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {

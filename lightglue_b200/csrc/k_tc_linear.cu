@@ -544,14 +544,8 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float a = v[8 * j8 + 2 * e], b = v[8 * j8 + 2 * e + 1];
-                  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-                  if (pass == 0) {
-                    w[e] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
-                  } else {
-                    const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha));
-                    const __nv_bfloat16 lb = __float2bfloat16_rn(b - __bfloat162float(hb));
-                    w[e] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
-                  }
+                  const uint32_t hi = pack_bf16x2(a, b);
+                  w[e] = pass == 0 ? hi : pack_bf16x2_lo(a, b, hi);
                 }
                 *reinterpret_cast<uint4*>(crow_lo + (j8 << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
               }
@@ -576,13 +570,8 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
                   const __half2 hh2 = __floats2half2_rn(a, b);
                   wh[e] = *reinterpret_cast<const uint32_t*>(&hh2);
                 } else {
-                  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-                  wh[e] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
-                  if (haslo) {
-                    const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha));
-                    const __nv_bfloat16 lb = __float2bfloat16_rn(b - __bfloat162float(hb));
-                    wl[e] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
-                  }
+                  wh[e] = pack_bf16x2(a, b);
+                  if (haslo) wl[e] = pack_bf16x2_lo(a, b, wh[e]);
                 }
               }
               const int chunk = (ci & 1) * 4 + j8;  // 16-byte chunk inside the 64-element box row
@@ -627,14 +616,11 @@ __global__ void __launch_bounds__(256) shadow_kernel(const float* __restrict__ x
   for (int c = threadIdx.x * 4; c < cols; c += 1024) {
     const float4 t = *reinterpret_cast<const float4*>(x + (long)row * cols + c);
     const float v[4] = {t.x, t.y, t.z, t.w};
-    __nv_bfloat16 h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      h[j] = __float2bfloat16_rn(v[j]);
-      l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
-    }
-    *reinterpret_cast<uint2*>(hi + (long)row * cols + c) = *reinterpret_cast<const uint2*>(h);
-    if (lo) *reinterpret_cast<uint2*>(lo + (long)row * cols + c) = *reinterpret_cast<const uint2*>(l);
+    uint2 h, l;
+    h.x = pack_bf16x2(v[0], v[1]); h.y = pack_bf16x2(v[2], v[3]);
+    l.x = pack_bf16x2_lo(v[0], v[1], h.x); l.y = pack_bf16x2_lo(v[2], v[3], h.y);
+    *reinterpret_cast<uint2*>(hi + (long)row * cols + c) = h;
+    if (lo) *reinterpret_cast<uint2*>(lo + (long)row * cols + c) = l;
   }
 }
 

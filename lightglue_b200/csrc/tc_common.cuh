@@ -212,6 +212,16 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool bf16) {
          ((uint32_t)(m >> 4) << 24);
 }
 
+// bf16 packing without per-element F2F conversions (those run on the slow XU pipe): one cvt.rn.bf16x2.f32 per pair,
+// and the hi values are recovered for the lo split with integer shifts
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {  // a -> low half
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_lo(float a, float b, uint32_t hi) {  // bf16(a - hi.a), bf16(b - hi.b)
+  return pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
