@@ -206,3 +206,35 @@ def test_log_assignment_matrix_tensor_core_variant():
     r0, r1, rs0, rs1 = oracle.filter_matches(ref, 0.1)
     assert torch.equal(m0.cpu(), r0) and torch.equal(m1.cpu(), r1)
     assert float((ms0.cpu() - rs0).abs().max()) < 1e-3
+
+
+def test_disk_n4096_against_oracle():
+    """BASELINE config 4 shape (DISK d=128, N=4096): index-exact tensor-core mode vs the CPU oracle."""
+    sd = synth.make_state_dict(input_dim=128)
+    data, _ = synth.make_pair(4096, d=128, b=1, seed=31)
+    ref = oracle.forward(sd, data)
+    m = LightGlue(features=None, input_dim=128, precision="bf16x3", depth_confidence=-1, width_confidence=-1)
+    m.load_state_dict(sd, strict=False)
+    out = m.cuda()(to_cuda(data))
+    flips = int((out["matches0"].cpu() != ref["matches0"]).sum()) + int((out["matches1"].cpu() != ref["matches1"]).sum())
+    dmax = float((out["matching_scores0"].cpu() - ref["matching_scores0"]).abs().max())
+    print(f"[bf16x3] disk n4096: flips={flips} max|dscore|={dmax:.2e} matches={int((ref['matches0'] > -1).sum())}")
+    assert flips == 0 and dmax < 1e-3
+
+
+def test_adaptive_n2048_default_flash_threshold():
+    """Adaptive depth/width at N=2048 with the reference's default CUDA+flash pruning threshold (1536, lightglue.py:
+    339-344, 658-662): pruning only runs while an image has more than 1536 points.  fp32 path vs the oracle."""
+    sd = synth.make_state_dict(adaptive=True)
+    data, _ = synth.make_pair(2048, b=1, seed=41)
+    ref = oracle.forward(sd, data, depth_confidence=0.95, width_confidence=0.99, pruning_threshold=1536)
+    m = LightGlue(features=None, precision="fp32")
+    m.load_state_dict(sd, strict=False)
+    m = m.cuda()
+    assert m.pruning_min_kpts(torch.device("cuda")) == 1536
+    out = m(to_cuda(data))
+    assert int(out["stop"]) == int(ref["stop"])
+    assert torch.equal(out["prune0"].cpu(), ref["prune0"]) and torch.equal(out["prune1"].cpu(), ref["prune1"])
+    assert torch.equal(out["matches0"].cpu(), ref["matches0"]) and torch.equal(out["matches1"].cpu(), ref["matches1"])
+    assert float((out["matching_scores0"].cpu() - ref["matching_scores0"]).abs().max()) < 1e-4
+    print("adaptive n2048: stop", out["stop"], "prune0 hist", torch.bincount(out["prune0"].flatten()).tolist())
