@@ -45,6 +45,7 @@ struct AttnParams {
   CUtensorMap vt_map;  // (Lp, 64, S*H)   box (64, 64, 1)
   __nv_bfloat16* ctxh; __nv_bfloat16* ctxl;
   int kv_shift;
+  int rows_per_cta;  // 256 (two query tiles per CTA) or 128 (one: small problems that would not fill the SMs)
   SeqState st;
   unsigned int* dbg;
 };
@@ -335,13 +336,13 @@ constexpr int B_STAGE_BYTES = K_TILE_BYTES + B_V_TILE_BYTES;  // 16 KB
 
 template <bool FAST>
 __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_constant__ AttnParams p) {
-  const int s = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * 2 * QT;
+  const int s = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * p.rows_per_cta;
   const int len_q = p.st.len[s];
   if (r0 >= len_q || lg_pair_stopped(p.st, s)) return;
   const int skv = (s + p.kv_shift) % p.st.S;
   const int len_kv = p.st.len[skv];
   const int nkv = (len_kv + KB - 1) / KB;
-  const int nt = (len_q - r0 > QT) ? 2 : 1;
+  const int nt = (p.rows_per_cta > QT && len_q - r0 > QT) ? 2 : 1;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -699,7 +700,12 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
   p.ctxh = b.ctxh; p.ctxl = b.ctxl; p.kv_shift = kv_shift; p.st = st; p.dbg = h->tc.dbg;
   static const int variant = getenv("LG_TC_ATTN_V") ? atoi(getenv("LG_TC_ATTN_V")) : 2;
   dim3 grid((st.Lp + 2 * QT - 1) / (2 * QT), LG_HEADS, st.S);
+  p.rows_per_cta = 2 * QT;
   if (variant == 2) {
+    if ((long)grid.x * grid.y * grid.z < 2 * 148) {  // fewer CTAs than resident slots: one query tile per CTA instead
+      p.rows_per_cta = QT;
+      grid.x = st.Lp / QT;
+    }
     constexpr int smem2 = 2 * Q_TILE_BYTES + B_KV_STAGES * B_STAGE_BYTES + 1024 + 256;
     static bool attr2 = false;
     if (!attr2) {
