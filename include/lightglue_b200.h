@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define LG_ABI_VERSION 1
+#define LG_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define LG_API __attribute__((visibility("default")))
@@ -67,6 +67,13 @@ typedef struct LgInputs {
   const float* oris1;
   int32_t pruning_threshold; /* pruning_min_kpts(device): prune an image only while it has more
                                 keypoints than this                                 (551, 658-662) */
+  /* Ragged batches (the reference pads + masks instead, lightglue.py:46-55, 256-262, 512-520):
+   * optional DEVICE arrays [B]; pair b uses only the first lens0[b] rows of kpts0/desc0 (<= M) and the
+   * first lens1[b] rows of kpts1/desc1 (<= N).  NULL = every pair uses M / N.  Rows past the length are
+   * never read; their outputs are matches -1, scores 0, prune 0.  A pair with a zero length is
+   * answered like the reference's empty-input branch (568-588): nothing matched, stop = 1. */
+  const int32_t* lens0;
+  const int32_t* lens1;
 } LgInputs;
 
 typedef struct LgOutputs {

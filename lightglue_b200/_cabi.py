@@ -8,7 +8,7 @@ from . import build as _build
 
 PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2}
 K_ATTENTION, K_LINEAR, K_ASSIGN, K_OTHER = 0, 1, 2, 3
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = (
     "lg_weight_blob_floats", "lg_create", "lg_destroy", "lg_workspace_bytes", "lg_forward", "lg_assign",
@@ -32,6 +32,7 @@ class LgInputs(C.Structure):
         ("size0", C.c_void_p), ("size1", C.c_void_p),
         ("scales0", C.c_void_p), ("oris0", C.c_void_p), ("scales1", C.c_void_p), ("oris1", C.c_void_p),
         ("pruning_threshold", C.c_int32),
+        ("lens0", C.c_void_p), ("lens1", C.c_void_p),
     ]
 
 

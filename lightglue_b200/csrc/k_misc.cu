@@ -13,8 +13,10 @@ __global__ void __launch_bounds__(256) posenc_kernel(PosencArgs a) {
   const int s = blockIdx.x, S = 2 * a.B;
   const bool im1 = s >= a.B;
   const int b = im1 ? s - a.B : s;
-  const int n = im1 ? a.N : a.M;
-  const float* kp = (im1 ? a.kpts1 : a.kpts0) + (long)b * n * 2;
+  const int stride = im1 ? a.N : a.M;                  // rows per pair in the (padded) input slabs
+  const int* lens = im1 ? a.lens1 : a.lens0;
+  const int n = lens ? min(max(lens[b], 0), stride) : stride;
+  const float* kp = (im1 ? a.kpts1 : a.kpts0) + (long)b * stride * 2;
   const float* size = im1 ? a.size1 : a.size0;
   const float* sc = im1 ? a.scales1 : a.scales0;
   const float* orr = im1 ? a.oris1 : a.oris0;
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(256) posenc_kernel(PosencArgs a) {
     const float x = (kp[i * 2] - shx) / scale, y = (kp[i * 2 + 1] - shy) / scale;  // (42)
     const float* w = a.wr + f * a.pos_dim;
     float pr = x * w[0] + y * w[1];
-    if (a.pos_dim == 4) pr += sc[(long)b * n + i] * w[2] + orr[(long)b * n + i] * w[3];  // (495-501)
+    if (a.pos_dim == 4) pr += sc[(long)b * stride + i] * w[2] + orr[(long)b * stride + i] * w[3];  // (495-501)
     float sn, cs;
     sincosf(pr, &sn, &cs);
     out[(long)i * 64 + f] = cs;
@@ -68,10 +70,11 @@ int misc_posenc(const PosencArgs& a, cudaStream_t stream) {
 }
 
 __global__ void pack_desc_kernel(const float* __restrict__ d0, const float* __restrict__ d1, float* __restrict__ out, int B,
-                                 int M, int N, int Lp, int d) {
+                                 int M, int N, int Lp, int d, const int* __restrict__ lens0, const int* __restrict__ lens1) {
   const int s = blockIdx.y, r = blockIdx.x;
   const bool im1 = s >= B;
-  const int n = im1 ? N : M;
+  const int* lens = im1 ? lens1 : lens0;
+  const int n = lens ? min(lens[im1 ? s - B : s], im1 ? N : M) : (im1 ? N : M);
   if (r >= n) return;
   const float* src = (im1 ? d1 + ((long)(s - B) * N + r) * d : d0 + ((long)s * M + r) * d);
   float* dst = out + ((long)s * Lp + r) * d;
@@ -79,32 +82,36 @@ __global__ void pack_desc_kernel(const float* __restrict__ d0, const float* __re
     *reinterpret_cast<float4*>(dst + c) = *reinterpret_cast<const float4*>(src + c);
 }
 
-int misc_pack_desc(const float* d0, const float* d1, float* out, int B, int M, int N, int Lp, int d, cudaStream_t stream) {
+int misc_pack_desc(const float* d0, const float* d1, float* out, int B, int M, int N, int Lp, int d, const int* lens0,
+                   const int* lens1, cudaStream_t stream) {
   const int mx = M > N ? M : N;
   if (mx == 0) return 0;
-  pack_desc_kernel<<<dim3(mx, 2 * B), 64, 0, stream>>>(d0, d1, out, B, M, N, Lp, d);
+  pack_desc_kernel<<<dim3(mx, 2 * B), 64, 0, stream>>>(d0, d1, out, B, M, N, Lp, d, lens0, lens1);
   LG_CHECK_LAUNCH();
   return 0;
 }
 
 __global__ void init_state_kernel(int* len, int* ind, int* prune, int* stop_layer, int* below, int n_below, int B, int M,
-                                  int N, int Lp) {
+                                  int N, int Lp, const int* lens0, const int* lens1) {
   const int s = blockIdx.x;
+  const int b = s >= B ? s - B : s;
+  const int l0 = lens0 ? min(max(lens0[b], 0), M) : M, l1 = lens1 ? min(max(lens1[b], 0), N) : N;
+  const int mylen = s >= B ? l1 : l0;
   if (threadIdx.x == 0) {
-    len[s] = s >= B ? N : M;
-    if (s < B) stop_layer[s] = 0;
+    len[s] = mylen;
+    if (s < B) stop_layer[s] = (l0 == 0 || l1 == 0) ? 1 : 0;  // an empty image: the pair never runs (568-588)
   }
   if (s == 0)
     for (int i = threadIdx.x; i < n_below; i += blockDim.x) below[i] = 0;
   for (int r = threadIdx.x; r < Lp; r += blockDim.x) {
     ind[(long)s * Lp + r] = r;
-    prune[(long)s * Lp + r] = 1;  // torch.ones_like(ind) (535-536)
+    prune[(long)s * Lp + r] = r < mylen ? 1 : 0;  // torch.ones_like(ind) (535-536); padding rows report 0
   }
 }
 
 int misc_init_state(int* len, int* ind, int* prune, int* stop_layer, int* below, int n_below, int B, int M, int N, int Lp,
-                    cudaStream_t stream) {
-  init_state_kernel<<<2 * B, 256, 0, stream>>>(len, ind, prune, stop_layer, below, n_below, B, M, N, Lp);
+                    const int* lens0, const int* lens1, cudaStream_t stream) {
+  init_state_kernel<<<2 * B, 256, 0, stream>>>(len, ind, prune, stop_layer, below, n_below, B, M, N, Lp, lens0, lens1);
   LG_CHECK_LAUNCH();
   return 0;
 }
@@ -173,12 +180,14 @@ __global__ void __launch_bounds__(1024) adapt_decide_kernel(AdaptArgs a, SeqStat
   const int len = a.len_in[s];
   const int tid = threadIdx.x;
   const int prev = st.stop_layer[pair];
-  const bool was_active = (prev == 0) || (prev == a.layer + 1);  // the sibling CTA may already have voted
+  // original sizes of the pair (ragged batches carry them per pair); an empty image never runs a layer
+  const int m0 = a.lens0 ? min(max(a.lens0[pair], 0), a.M) : a.M, n0 = a.lens1 ? min(max(a.lens1[pair], 0), a.N) : a.N;
+  const bool was_active = m0 > 0 && n0 > 0 && ((prev == 0) || (prev == a.layer + 1));  // the sibling CTA may already have voted
   bool stop = false;
   if (was_active && a.tok_w) {
     // ratio_confident = 1 - (#conf < thr) / (m + n) > depth_confidence  (655-656); denominator is the
     // ORIGINAL m + n, numerator counts surviving points only (549)
-    const float ratio = 1.0f - (float)a.below[pair] / (float)(a.M + a.N);
+    const float ratio = 1.0f - (float)a.below[pair] / (float)(m0 + n0);
     stop = ratio > a.depth_conf;
   }
   const bool do_prune = was_active && !stop && a.mat_w && len > a.pruning_threshold;
@@ -499,6 +508,11 @@ __global__ void assign_filter_kernel(AssignArgs a, SeqState st) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = st.len[b], n = st.len[b + st.B];
   const long rbase = (long)b * st.Lp;
+  if (m == 0 || n == 0) {  // an empty image: nothing to match against (568-588); the arg-max slots hold no data
+    if (idx < m) { a.ms0c[rbase + idx] = 0.f; a.m0c[rbase + idx] = -1; }
+    if (idx < n) { a.ms1c[rbase + idx] = 0.f; a.m1c[rbase + idx] = -1; }
+    return;
+  }
   if (idx < m) {
     const int j = a.rowarg[(rbase + idx) * a.nt];
     const bool mutual = a.colarg[(rbase + j) * a.nt] == idx;

@@ -392,7 +392,9 @@ extern "C" int lg_forward(LgHandle* h, const LgInputs* in, const LgOutputs* out,
   const int L = h->cfg.n_layers, Lp = w.Lp;
   const bool fp32 = h->cfg.precision == LG_PREC_FP32;
 
-  RC(misc_init_state(w.lena, w.inda, w.prune, w.stop_layer, w.below, L * B, B, M, N, Lp, stream));
+  if (out->log_assignment && (in->lens0 || in->lens1))
+    return lg_set_error("lg_forward: log_assignment is defined for dense batches only (no lens0/lens1)");
+  RC(misc_init_state(w.lena, w.inda, w.prune, w.stop_layer, w.below, L * B, B, M, N, Lp, in->lens0, in->lens1, stream));
   h->launches += 1;
   float *x = w.xa, *x_alt = w.xb, *cs = w.csa, *cs_alt = w.csb;
   int *len = w.lena, *len_alt = w.lenb, *ind = w.inda, *ind_alt = w.indb;
@@ -401,17 +403,17 @@ extern "C" int lg_forward(LgHandle* h, const LgInputs* in, const LgOutputs* out,
   {  // positional encoding, cached for all layers (lightglue.py:523-525)
     Timer t(h, LG_K_OTHER, stream);
     PosencArgs pa{in->kpts0, in->kpts1, in->size0, in->size1, in->scales0, in->oris0, in->scales1, in->oris1,
-                  h->wpk + h->o_wr, h->cfg.pos_dim, B, M, N, Lp, cs};
+                  h->wpk + h->o_wr, h->cfg.pos_dim, B, M, N, Lp, cs, in->lens0, in->lens1};
     RC(misc_posenc(pa, stream));
     h->launches += 1;
   }
   // descriptors -> residual stream (optionally through input_proj, lightglue.py:521-522)
   if (h->cfg.input_dim == (int)D) {
-    RC(misc_pack_desc(in->desc0, in->desc1, x, B, M, N, Lp, D, stream));
+    RC(misc_pack_desc(in->desc0, in->desc1, x, B, M, N, Lp, D, in->lens0, in->lens1, stream));
     h->launches += 1;
     if (!fp32) { RC(tc_refresh_shadow(h, w.tc, x, st, stream)); h->launches += 1; }
   } else {
-    RC(misc_pack_desc(in->desc0, in->desc1, w.hbuf, B, M, N, Lp, h->cfg.input_dim, stream));
+    RC(misc_pack_desc(in->desc0, in->desc1, w.hbuf, B, M, N, Lp, h->cfg.input_dim, in->lens0, in->lens1, stream));
     h->launches += 1;
     Timer t(h, LG_K_LINEAR, stream);
     if (fp32) {
@@ -474,6 +476,7 @@ extern "C" int lg_forward(LgHandle* h, const LgInputs* in, const LgOutputs* out,
     a.mat_w = prune ? as + AO_MW : nullptr; a.mat_b = prune ? as + AO_MB : nullptr;
     a.thr = h->thr[i]; a.depth_conf = h->cfg.depth_confidence; a.width_conf = h->cfg.width_confidence;
     a.layer = i; a.M = M; a.N = N; a.pruning_threshold = in->pruning_threshold;
+    a.lens0 = in->lens0; a.lens1 = in->lens1;
     a.keep = w.keep; a.below = w.below + (size_t)i * B; a.stop_layer = w.stop_layer;
     a.len_in = len; a.len_out = prune ? len_alt : len; a.pos = w.pos; a.did_prune = w.did_prune;
     RC(misc_adapt_score(a, st, stream));
@@ -509,9 +512,10 @@ extern "C" int lg_assign(LgHandle* h, int32_t layer, int32_t B, int32_t M, int32
   carve(h, B, M, N, (char*)workspace, &w);
   if (!workspace || ws_bytes < w.bytes) return lg_set_error("lg_assign: workspace too small");
   h->launches = 0;
-  RC(misc_init_state(w.lena, w.inda, w.prune, w.stop_layer, w.below, h->cfg.n_layers * B, B, M, N, w.Lp, stream));
+  RC(misc_init_state(w.lena, w.inda, w.prune, w.stop_layer, w.below, h->cfg.n_layers * B, B, M, N, w.Lp, nullptr, nullptr,
+                     stream));
   RC(misc_finalize_stop(w.stop_layer, B, layer + 1, stream));  // selects log_assignment[layer] for every pair
-  RC(misc_pack_desc(x0, x1, w.xa, B, M, N, w.Lp, D, stream));
+  RC(misc_pack_desc(x0, x1, w.xa, B, M, N, w.Lp, D, nullptr, nullptr, stream));
   h->launches += 3;
   SeqState st{2 * B, B, w.Lp, w.lena, w.stop_layer};
   if (h->cfg.precision != LG_PREC_FP32) { RC(tc_refresh_shadow(h, w.tc, w.xa, st, stream)); h->launches += 1; }

@@ -66,13 +66,16 @@ struct PosencArgs {
   const float* wr;                              // [32, pos_dim]
   int pos_dim, B, M, N, Lp;
   float* cs;                                    // [S, Lp, 64]
+  const int* lens0; const int* lens1;           // [B] valid rows per pair, or null (= M / N)
 };
 int misc_posenc(const PosencArgs& a, cudaStream_t stream);
 // descriptors [B,M,d] / [B,N,d] -> padded [S, Lp, d] fp32
-int misc_pack_desc(const float* d0, const float* d1, float* out, int B, int M, int N, int Lp, int d, cudaStream_t stream);
-// len[s] = M or N, ind[s][r] = r, prune[s][r] = 1, stop_layer = 0, below = 0
+int misc_pack_desc(const float* d0, const float* d1, float* out, int B, int M, int N, int Lp, int d, const int* lens0,
+                   const int* lens1, cudaStream_t stream);
+// len[s] = lens[s] (or M / N), ind[s][r] = r, prune[s][r] = 1 for live rows, below = 0, stop_layer = 0 -- or 1 for a
+// pair with an empty image (answered like lightglue.py:568-588: no layer runs, nothing matches)
 int misc_init_state(int* len, int* ind, int* prune, int* stop_layer, int* below, int n_below, int B, int M, int N, int Lp,
-                    cudaStream_t stream);
+                    const int* lens0, const int* lens1, cudaStream_t stream);
 
 struct AdaptArgs {
   const float* x;                   // [S, Lp, 256] fp32 residual stream
@@ -81,6 +84,7 @@ struct AdaptArgs {
   float thr;                        // confidence_thresholds[i]
   float depth_conf, width_conf;
   int layer, M, N, pruning_threshold;
+  const int* lens0; const int* lens1;  // [B] original lengths of a ragged batch, or null (= M / N)
   unsigned char* keep;              // [S, Lp]
   int* below;                       // [B] (this layer's slot)
   int* stop_layer;                  // [B] (written)

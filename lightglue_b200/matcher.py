@@ -243,6 +243,11 @@ class LightGlue(nn.Module):
         data = {"image0": {"keypoints" [B,M,2], "descriptors" [B,M,D], optional "image_size" [B,2],
         optional "scales"/"oris" [B,M]}, "image1": {...}}  ->  dict with matches0/1, matching_scores0/1,
         matches, scores, stop, prune0/1.
+
+        Extension (ragged batches): an optional "num_keypoints" [B] integer tensor per image
+        says how many leading rows of that pair are real keypoints; the rest is padding that no kernel
+        reads (the reference pads + masks instead, 46-55, 256-262, 512-520).  Padding rows come back as
+        matches -1 / scores 0 / prune 0; every pair's result equals its own B=1 call.
         """
         for key in self.required_data_keys:
             assert key in data, f"Missing key {key} in data"
@@ -271,6 +276,15 @@ class LightGlue(nn.Module):
             return s.expand(b, 2).contiguous() if s.dim() == 1 else s.contiguous()
 
         s0, s1 = size_tensor(s0), size_tensor(s1)
+
+        def len_tensor(t, cap):
+            if t is None:
+                return None
+            t = torch.as_tensor(t, device=device).to(torch.int32).reshape(-1).contiguous()
+            assert t.numel() == b, "num_keypoints must hold one count per pair"
+            return t.clamp(0, cap)
+
+        l0, l1 = len_tensor(d0.get("num_keypoints"), m), len_tensor(d1.get("num_keypoints"), n)
         sc0 = or0 = sc1 = or1 = None
         if self.conf.add_scale_ori:
             sc0, or0, sc1, or1 = f32(d0["scales"]), f32(d0["oris"]), f32(d1["scales"]), f32(d1["oris"])
@@ -285,7 +299,7 @@ class LightGlue(nn.Module):
             handle = self._get_handle(device)
             lib = _cabi.load()
             use_graph = bool(self.conf.cuda_graph) and m > 0 and n > 0 and not self.timing
-            key = (device.index, b, m, n, prune, pruning_th, s0 is None, s1 is None)
+            key = (device.index, b, m, n, prune, pruning_th, s0 is None, s1 is None, l0 is None, l1 is None)
             slot = self._graphs.get(key) if use_graph else None
             if slot is None:
                 ws = self._workspace(handle, device, b, m, n)
@@ -301,11 +315,11 @@ class LightGlue(nn.Module):
                     "pairs": torch.empty(b, cap, 2, dtype=torch.int64, device=device),
                     "pscores": torch.empty(b, cap, dtype=torch.float32, device=device),
                 }
-                ins = [k0, k1, x0, x1, s0, s1, sc0, or0, sc1, or1]
+                ins = [k0, k1, x0, x1, s0, s1, sc0, or0, sc1, or1, l0, l1]
                 if use_graph:  # static input buffers the graph reads from
                     ins = [None if t is None else t.clone() for t in ins]
                 ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
-                inp = _cabi.LgInputs(b, m, n, *[ptr(t) for t in ins], pruning_th)
+                inp = _cabi.LgInputs(b, m, n, *[ptr(t) for t in ins[:10]], pruning_th, ptr(ins[10]), ptr(ins[11]))
                 out = _cabi.LgOutputs(
                     ptr(io["m0"]), ptr(io["m1"]), ptr(io["ms0"]), ptr(io["ms1"]), io["meta"][0].data_ptr(), ptr(io["pr0"]),
                     ptr(io["pr1"]), io["meta"][1].data_ptr(), ptr(io["pairs"]), ptr(io["pscores"]), None,
@@ -337,7 +351,7 @@ class LightGlue(nn.Module):
                     launch()
             if use_graph:
                 graph, ins, io, _keep = slot
-                for dst, src in zip(ins, [k0, k1, x0, x1, s0, s1, sc0, or0, sc1, or1]):
+                for dst, src in zip(ins, [k0, k1, x0, x1, s0, s1, sc0, or0, sc1, or1, l0, l1]):
                     if dst is not None:
                         dst.copy_(src, non_blocking=True)
                 graph.replay()
@@ -359,7 +373,7 @@ class LightGlue(nn.Module):
         else:  # reference 616-617: float tensors filled with n_layers
             prune0 = torch.full((b, m), float(self.conf.n_layers), dtype=torch.float32, device=device)
             prune1 = torch.full((b, n), float(self.conf.n_layers), dtype=torch.float32, device=device)
-        return {
+        res = {
             "matches0": m0,
             "matches1": m1,
             "matching_scores0": ms0,
@@ -370,6 +384,9 @@ class LightGlue(nn.Module):
             "prune0": prune0,
             "prune1": prune1,
         }
+        if l0 is not None or l1 is not None:  # ragged batch: per-pair exit layers for split_outputs
+            res["stops"] = [int(v) for v in meta_h[0].tolist()]
+        return res
 
     # ------------------------------------------------------------------ extras used by tests / bench
     def log_assignment_matrix(self, layer: int, desc0: torch.Tensor, desc1: torch.Tensor):

@@ -68,3 +68,86 @@ def test_forward_rejects_missing_keys_and_cpu_tensors():
         m({"image0": data["image0"]})
     with pytest.raises(RuntimeError):  # no CPU path: fail loudly
         m(data)
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of the C-ABI structs as gcc lays them out == the ctypes mirrors in _cabi.py."""
+    import ctypes as C
+    import subprocess
+
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "lightglue_b200.h"\n'
+        "int main(void) {\n"
+        '  printf("%zu %zu %zu %zu %zu %zu %zu %d\\n", sizeof(LgConfig), sizeof(LgInputs), sizeof(LgOutputs),\n'
+        "         offsetof(LgInputs, pruning_threshold), offsetof(LgInputs, lens0), offsetof(LgInputs, lens1),\n"
+        "         offsetof(LgOutputs, log_assignment), LG_ABI_VERSION);\n"
+        "  return 0;\n}\n"
+    )
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    want = [
+        C.sizeof(_cabi.LgConfig), C.sizeof(_cabi.LgInputs), C.sizeof(_cabi.LgOutputs),
+        _cabi.LgInputs.pruning_threshold.offset, _cabi.LgInputs.lens0.offset, _cabi.LgInputs.lens1.offset,
+        _cabi.LgOutputs.log_assignment.offset, _cabi.ABI_VERSION,
+    ]
+    assert got == want
+
+
+def test_ragged_padding_and_splitting_host_logic():
+    from lightglue_b200.ragged import pad_pairs, split_outputs
+
+    pairs = []
+    for m, n in ((5, 3), (2, 7), (0, 4)):
+        data, _ = synth.make_pair(max(m, n, 1), b=1, seed=m + n, m=max(m, 1))
+        f0 = {k: (v[:, :m] if v.dim() == 3 else v) for k, v in data["image0"].items()}
+        f1 = {k: (v[0, :n] if v.dim() == 3 else v) for k, v in data["image1"].items()}  # unbatched form
+        pairs.append({"image0": f0, "image1": f1})
+    data = pad_pairs(pairs)
+    assert data["image0"]["keypoints"].shape == (3, 5, 2) and data["image1"]["descriptors"].shape == (3, 7, 256)
+    assert data["image0"]["num_keypoints"].tolist() == [5, 2, 0] and data["image1"]["num_keypoints"].tolist() == [3, 7, 4]
+    assert data["image0"]["image_size"].shape == (3, 2)
+    assert torch.equal(data["image1"]["keypoints"][0, :3], pairs[0]["image1"]["keypoints"])
+    assert float(data["image0"]["descriptors"][1, 2:].abs().sum()) == 0.0  # zero padding
+    out = {
+        "matches0": torch.full((3, 5), -1), "matches1": torch.full((3, 7), -1),
+        "matching_scores0": torch.zeros(3, 5), "matching_scores1": torch.zeros(3, 7),
+        "matches": [torch.zeros(0, 2, dtype=torch.int64)] * 3, "scores": [torch.zeros(0)] * 3,
+        "prune0": torch.ones(3, 5), "prune1": torch.ones(3, 7), "stop": 9, "stops": [9, 4, 1],
+    }
+    parts = split_outputs(out, data["image0"]["num_keypoints"], data["image1"]["num_keypoints"])
+    assert [p["matches0"].shape[1] for p in parts] == [5, 2, 0] and [p["matches1"].shape[1] for p in parts] == [3, 7, 4]
+    assert [p["stop"] for p in parts] == [9, 4, 1] and isinstance(parts[0]["matches"], list)
+    with pytest.raises(ValueError):
+        pairs[1]["image0"].pop("image_size")
+        pad_pairs(pairs)
+
+
+def test_caller_glue_rbd_batch_to_device_match_pair():
+    """utils.rbd / batch_to_device / match_pair behave like the reference's (utils.py:41-69, 150-165)."""
+    import numpy as np
+
+    from lightglue_b200 import utils
+
+    d = {"a": torch.arange(6).reshape(1, 3, 2), "b": [torch.ones(2)], "stop": 7, "n": np.zeros((1, 4)), "s": "name"}
+    r = utils.rbd(d)
+    assert r["a"].shape == (3, 2) and torch.equal(r["b"], torch.ones(2)) and r["stop"] == 7 and r["n"].shape == (4,)
+    assert r["s"] == "name"
+    moved = utils.batch_to_device({"x": torch.ones(2, requires_grad=True), "l": [torch.zeros(1)], "k": "v", "i": 3}, "cpu")
+    assert not moved["x"].requires_grad and isinstance(moved["l"], list) and moved["k"] == "v" and moved["i"] == 3
+
+    class Extractor:
+        def extract(self, img, **conf):
+            n = int(img.shape[-1])
+            return {"keypoints": torch.zeros(1, n, 2), "descriptors": torch.zeros(1, n, 256),
+                    "image_size": torch.tensor([[float(n), 1.0]]), "resize": conf.get("resize")}
+
+    def matcher(data):
+        m, n = data["image0"]["keypoints"].shape[1], data["image1"]["keypoints"].shape[1]
+        return {"matches0": torch.full((1, m), -1), "matches1": torch.full((1, n), -1),
+                "matches": [torch.zeros(0, 2, dtype=torch.int64)], "scores": [torch.zeros(0)], "stop": 3}
+
+    f0, f1, m01 = utils.match_pair(Extractor(), matcher, torch.zeros(1, 8, 5), torch.zeros(1, 8, 9), resize=512)
+    assert f0["keypoints"].shape == (5, 2) and f1["descriptors"].shape == (9, 256) and f0["resize"] == 512
+    assert m01["matches0"].shape == (5,) and m01["matches"].shape == (0, 2) and m01["stop"] == 3
