@@ -59,6 +59,19 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic(kernel: str, batch: int, precision: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), or None
+    when this run's workload is not the one that was profiled."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        d = json.load(f)
+    if d.get("workload") != f"superpoint_n{N_KPTS}_l9_prune_off_b{batch}" or d.get("precision") != precision:
+        return None
+    return d.get(kernel, {}).get("bytes_per_launch")
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -315,7 +328,8 @@ def main():
             ach = attention_flops_per_launch(B) / ((att_ms / att_n) / 1000.0) / 1e12
             peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
             roofline = {"kernel": "attention", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": None, "peak_source": how + ", sustained (kernel timed inside a long step)",
+                        "frac": ach / peak, "traffic": profiled_traffic("attention", B, args.precision),
+                        "peak_source": how + ", sustained (kernel timed inside a long step)",
                         "flops_per_launch": attention_flops_per_launch(B), "avg_launch_ms": att_ms / att_n}
 
     # ---- assignment kernel, materialising variant (MatchAssignment.forward's declared output, lightglue.py:296):
@@ -338,7 +352,8 @@ def main():
             abytes = 18.9e6 * B
             ach = abytes / ((am_ms / am_n) / 1000.0) / 1e9
             roofline_assign = {"kernel": "assignment sweep 2 (+ log-assignment matrix write)", "bound": "hbm", "achieved": ach,
-                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                               "traffic": profiled_traffic("assign_matrix", B, args.precision),
                                "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": am_ms / am_n, "peak_source": how}
         del xa, xb
 

@@ -343,19 +343,29 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
         const int ncols = p.st.len[ti.sel] - ti.n_tile * BN - half * HCOLS;  // live columns of this warp's half
         const int slot = ti.n_tile * 2 + half;
         if (EPI == TEPI_LSE) {
-          float m = -INFINITY, se = 0.f;  // online (max, sum-exp)
+          // online (max, sum-exp) in base 2: exp(x - m) = ex2(x * log2e - m * log2e), one FFMA + one MUFU per element
+          constexpr float L2E = 1.4426950408889634f;
+          float m = -INFINITY, se = 0.f;
           for (int c0 = 0; c0 < HCOLS && c0 < ncols; c0 += 32) {
             tmem_ld32(tl + c0, raw);
             tmem_ld_wait();
-            float cm = -INFINITY;
+            if (c0 + 32 > ncols) {  // ragged last chunk: padding columns count as -inf
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (c0 + j >= ncols) raw[j] = 0xff800000u;
-              cm = fmaxf(cm, __uint_as_float(raw[j]));
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j >= ncols) raw[j] = 0xff800000u;
             }
-            if (cm > m) { se *= expf(m - cm); m = cm; }
+            float cm = __uint_as_float(raw[0]);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) se += expf(__uint_as_float(raw[j]) - m);
+            for (int j = 1; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(raw[j]));
+            if (cm > m) { se *= ex2_approx((m - cm) * L2E); m = cm; }
+            const float mb = -m * L2E;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              s0 += ex2_approx(fmaf(__uint_as_float(raw[j]), L2E, mb));
+              s1 += ex2_approx(fmaf(__uint_as_float(raw[j + 1]), L2E, mb));
+            }
+            se += s0 + s1;
           }
           if (live) reinterpret_cast<float2*>(p.part)[grow * p.part_stride + slot] = make_float2(m, se);
         } else {
@@ -365,9 +375,14 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
           // the matrix is written from the image0 side only (rows = image0 points, columns = image1 points)
           const bool write_mat = NSLOT == 1 && p.logmat != nullptr && ti.s < p.st.B;
           float best = -INFINITY; int arg = 0;
+          const int col0 = ti.n_tile * BN + half * HCOLS;
+          const int rbase = ti.r0 + quarter * 32;                 // first row of this warp inside its sequence
+          const int rows_ok = min(32, ti.len - rbase);            // live rows of this warp (may be <= 0)
+          const long pitch = p.mat_n + 1;
           for (int c0 = 0; c0 < HCOLS && c0 < ncols; c0 += 32) {
             tmem_ld32(tl + c0, raw);
             tmem_ld_wait();
+            const int nlive = ncols - c0;  // >= 32 on every chunk but a ragged last one
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 c4v = __ldg(reinterpret_cast<const float4*>(ct + c0) + j4);
@@ -375,12 +390,13 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
                 const int j = j4 * 4 + jj;
-                const float sc = fmaf(2.f, __uint_as_float(raw[j]), cc[jj]);
-                if (c0 + j < ncols && sc > best) { best = sc; arg = ti.n_tile * BN + half * HCOLS + c0 + j; }  // first max wins
+                float sc = fmaf(2.f, __uint_as_float(raw[j]), cc[jj]);
                 raw[j] = __float_as_uint(sc + rterm);
+                if (j >= nlive) sc = -INFINITY;                    // uniform, false on full chunks
+                if (sc > best) { best = sc; arg = col0 + c0 + j; }  // ascending j: first max wins
               }
             }
-            if (write_mat) {
+            if (write_mat && rows_ok > 0) {
               // stage the 32 x 32 block (swizzled), then every row leaves as one 128-byte store of the warp:
               // the (N+1)-float row pitch of the reference's matrix is only 4-byte aligned, so no TMA here
               __syncwarp();
@@ -388,14 +404,18 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
               for (int j4 = 0; j4 < 8; ++j4)
                 *reinterpret_cast<uint4*>(arow + ((j4 ^ sw) << 4)) = make_uint4(raw[4 * j4], raw[4 * j4 + 1], raw[4 * j4 + 2], raw[4 * j4 + 3]);
               __syncwarp();
-              const int cj = ti.n_tile * BN + half * HCOLS + c0 + lane;   // this lane's column
-              const int rbase = ti.r0 + quarter * 32;
-              float* mo = p.logmat + ((long)ti.s * (p.mat_m + 1) + rbase) * (p.mat_n + 1) + cj;
-              const bool col_ok = c0 + lane < ncols;
-#pragma unroll 8
-              for (int rr = 0; rr < 32; ++rr) {
-                const float val = *reinterpret_cast<const float*>(boxA + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2)));
-                if (col_ok && rbase + rr < ti.len) mo[(long)rr * (p.mat_n + 1)] = val;
+              if (lane < nlive) {  // this lane's column exists
+                float* mo = p.logmat + ((long)ti.s * (p.mat_m + 1) + rbase) * pitch + (col0 + c0 + lane);
+                const uint8_t* src = boxA + ((lane & 3) << 2);
+                const int l4 = lane >> 2;
+                if (rows_ok == 32) {
+#pragma unroll
+                  for (int rr = 0; rr < 32; ++rr, mo += pitch)
+                    *mo = *reinterpret_cast<const float*>(src + rr * 128 + ((l4 ^ (rr & 7)) << 4));
+                } else {
+                  for (int rr = 0; rr < rows_ok; ++rr, mo += pitch)
+                    *mo = *reinterpret_cast<const float*>(src + rr * 128 + ((l4 ^ (rr & 7)) << 4));
+                }
               }
             }
           }
