@@ -134,6 +134,17 @@ LG_API int lg_forward(LgHandle* h, const LgInputs* in, const LgOutputs* out, voi
 LG_API int lg_assign(LgHandle* h, int32_t layer, int32_t B, int32_t M, int32_t N, const float* x0, const float* x1,
               const LgOutputs* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Kernel-level entry point (unit tests / ncu): Attention.forward (lightglue.py:97-137) on heads that are
+ * already projected and rotated, through the attention kernel lg_forward uses in this handle's precision
+ * mode.  q0, k0, v0 [B, 4, M, 64] and q1, k1, v1 [B, 4, N, 64] fp32 device (the reference's [B, H, N, dh]
+ * layout, 166-167 / 207).  cross == 0: ctx0 = softmax(q0 k0^T / 8) v0, ctx1 likewise for image 1
+ * (SelfBlock, 170); cross != 0: ctx0 = softmax(q0 k1^T / 8) v1 and ctx1 = softmax(q1 k0^T / 8) v0
+ * (CrossBlock, 210-214).  ctx0 [B, M, 256], ctx1 [B, N, 256] fp32, heads concatenated h-major (171 / 208).
+ * The tensor-core modes round q, k, v to fp16 like the reference's flash path (116-121). */
+LG_API int lg_attention(LgHandle* h, int32_t B, int32_t M, int32_t N, int32_t cross, const float* q0, const float* k0,
+                 const float* v0, const float* q1, const float* k1, const float* v1, float* ctx0, float* ctx1,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* Number of kernel launches issued by the last lg_forward / lg_assign on this handle. */
 LG_API int64_t lg_last_launch_count(const LgHandle* h);
 

@@ -11,7 +11,7 @@ K_ATTENTION, K_LINEAR, K_ASSIGN, K_OTHER = 0, 1, 2, 3
 ABI_VERSION = 2
 
 EXPORTS = (
-    "lg_weight_blob_floats", "lg_create", "lg_destroy", "lg_workspace_bytes", "lg_forward", "lg_assign",
+    "lg_weight_blob_floats", "lg_create", "lg_destroy", "lg_workspace_bytes", "lg_forward", "lg_assign", "lg_attention",
     "lg_last_launch_count", "lg_timing_enable", "lg_kernel_time_ms", "lg_last_error", "lg_build_info",
     "lg_debug_timeout_code",
 )
@@ -77,6 +77,8 @@ def load():
         C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(LgOutputs),
         C.c_void_p, C.c_size_t, C.c_void_p,
     ]
+    lib.lg_attention.restype = C.c_int
+    lib.lg_attention.argtypes = [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 8 + [C.c_void_p, C.c_size_t, C.c_void_p]
     lib.lg_last_launch_count.restype = C.c_int64
     lib.lg_last_launch_count.argtypes = [C.c_void_p]
     lib.lg_timing_enable.restype = C.c_int

@@ -2,6 +2,9 @@
 // adaptive depth/width machinery (token confidence, stop vote, order-preserving compaction) and the
 // assignment tail (dual-softmax log-assignment, mutual-nearest filter, output assembly).
 // lightglue.py line numbers refer to /root/reference/lightglue/lightglue.py.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "lg_internal.h"
 
 // ------------------------------------------------------------------------------------------------
@@ -671,6 +674,53 @@ __global__ void export_stop_prune_kernel(const int* stop_layer, const int* prune
 int misc_export_stop_prune(const int* stop_layer, const int* prune, int* stop_out, int* prune0, int* prune1, int B, int M,
                            int N, int Lp, cudaStream_t stream) {
   export_stop_prune_kernel<<<2 * B, 256, 0, stream>>>(stop_layer, prune, stop_out, prune0, prune1, B, M, N, Lp);
+  LG_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lg_attention plumbing (kernel-level entry point): reference head layout <-> kernel operand layouts
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) attn_pack_kernel(AttnIoArgs a) {
+  const int r = blockIdx.x, hh = blockIdx.y, s = blockIdx.z, d = threadIdx.x;
+  const bool im1 = s >= a.B;
+  const int b = im1 ? s - a.B : s, n = im1 ? a.N : a.M;
+  if (r >= n) return;
+  const long src = (((long)b * LG_HEADS + hh) * n + r) * LG_HDIM + d;
+  const float q = (im1 ? a.q1 : a.q0)[src], k = (im1 ? a.k1 : a.k0)[src], v = (im1 ? a.v1 : a.v0)[src];
+  const long sh = (long)s * LG_HEADS + hh;
+  const long dst = (sh * a.Lp + r) * LG_HDIM + d;
+  if (a.qf) { a.qf[dst] = q; a.kf[dst] = k; a.vf[dst] = v; }
+  if (a.qh) {
+    reinterpret_cast<__half*>(a.qh)[dst] = __float2half_rn(q);
+    reinterpret_cast<__half*>(a.kh)[dst] = __float2half_rn(k);
+    reinterpret_cast<__half*>(a.vth)[(sh * LG_HDIM + d) * a.Lp + r] = __float2half_rn(v);
+  }
+}
+int misc_attn_pack(const AttnIoArgs& a, cudaStream_t stream) {
+  const int mx = a.M > a.N ? a.M : a.N;
+  attn_pack_kernel<<<dim3(mx, LG_HEADS, 2 * a.B), 64, 0, stream>>>(a);
+  LG_CHECK_LAUNCH();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) attn_unpack_kernel(AttnIoArgs a) {
+  const int r = blockIdx.x, s = blockIdx.y, c = threadIdx.x;
+  const bool im1 = s >= a.B;
+  const int b = im1 ? s - a.B : s, n = im1 ? a.N : a.M;
+  if (r >= n) return;
+  const long src = ((long)s * a.Lp + r) * LG_DIM + c;
+  float v;
+  if (a.ctxf) v = a.ctxf[src];
+  else {
+    v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.ctxh)[src]);
+    if (a.ctxl) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.ctxl)[src]);
+  }
+  (im1 ? a.out1 : a.out0)[((long)b * n + r) * LG_DIM + c] = v;
+}
+int misc_attn_unpack(const AttnIoArgs& a, cudaStream_t stream) {
+  const int mx = a.M > a.N ? a.M : a.N;
+  attn_unpack_kernel<<<dim3(mx, 2 * a.B), 256, 0, stream>>>(a);
   LG_CHECK_LAUNCH();
   return 0;
 }

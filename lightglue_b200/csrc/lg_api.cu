@@ -521,3 +521,34 @@ extern "C" int lg_assign(LgHandle* h, int32_t layer, int32_t B, int32_t M, int32
   if (h->cfg.precision != LG_PREC_FP32) { RC(tc_refresh_shadow(h, w.tc, w.xa, st, stream)); h->launches += 1; }
   return run_assign(h, w, st, w.xa, w.inda, M, N, out, stream);
 }
+
+extern "C" int lg_attention(LgHandle* h, int32_t B, int32_t M, int32_t N, int32_t cross, const float* q0, const float* k0,
+                            const float* v0, const float* q1, const float* k1, const float* v1, float* ctx0, float* ctx1,
+                            void* workspace, size_t ws_bytes, void* stream_) {
+  if (!h || !q0 || !k0 || !v0 || !q1 || !k1 || !v1 || !ctx0 || !ctx1) return lg_set_error("lg_attention: null argument");
+  if (B <= 0 || M <= 0 || N <= 0) return lg_set_error("lg_attention: bad shape");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  Workspace w;
+  carve(h, B, M, N, (char*)workspace, &w);
+  if (!workspace || ws_bytes < w.bytes) return lg_set_error("lg_attention: workspace too small");
+  h->launches = 0;
+  RC(misc_init_state(w.lena, w.inda, w.prune, w.stop_layer, w.below, h->cfg.n_layers * B, B, M, N, w.Lp, nullptr, nullptr,
+                     stream));
+  SeqState st{2 * B, B, w.Lp, w.lena, w.stop_layer};
+  const bool fp32 = h->cfg.precision == LG_PREC_FP32;
+  AttnIoArgs a{};
+  a.q0 = q0; a.k0 = k0; a.v0 = v0; a.q1 = q1; a.k1 = k1; a.v1 = v1;
+  a.B = B; a.M = M; a.N = N; a.Lp = w.Lp;
+  if (fp32) { a.qf = w.q; a.kf = w.k; a.vf = w.v; a.ctxf = w.ctx; }
+  else { a.qh = w.tc.q; a.kh = w.tc.k; a.vth = w.tc.vt; a.ctxh = w.tc.ctxh; a.ctxl = w.tc.ctxl; }
+  a.out0 = ctx0; a.out1 = ctx1;
+  RC(misc_attn_pack(a, stream));
+  {
+    Timer t(h, LG_K_ATTENTION, stream);
+    if (fp32) RC(simt_attention(w.q, w.k, w.v, w.ctx, cross ? B : 0, st, stream));
+    else RC(tc_attention(h, w.tc, st, cross ? B : 0, w.tc.k, stream));
+  }
+  RC(misc_attn_unpack(a, stream));
+  h->launches += fp32 ? 4 : 3;  // init + pack + (attention counted by tc_attention) + unpack
+  return 0;
+}

@@ -105,6 +105,20 @@ struct GatherArgs {
 int misc_adapt_gather(const GatherArgs& a, const SeqState& st, cudaStream_t stream);
 int misc_finalize_stop(int* stop_layer, int B, int n_layers, cudaStream_t stream);
 
+// lg_attention plumbing: [B, H, n, 64] fp32 heads -> the attention kernels' operand layouts, and back.
+// fp32 mode: qf/kf/vf fp32 [S, H, Lp, 64].  Tensor-core modes: qh/kh fp16 [S, H, Lp, 64], vth fp16 [S, H, 64, Lp].
+struct AttnIoArgs {
+  const float *q0, *k0, *v0, *q1, *k1, *v1;
+  int B, M, N, Lp;
+  float *qf, *kf, *vf;
+  void *qh, *kh, *vth;          // __half*
+  const float* ctxf;            // fp32 mode: [S, Lp, 256]
+  const void *ctxh, *ctxl;      // tensor-core modes: bf16 hi (/ lo) [S*Lp, 256]
+  float *out0, *out1;           // [B, M, 256], [B, N, 256]
+};
+int misc_attn_pack(const AttnIoArgs& a, cudaStream_t stream);
+int misc_attn_unpack(const AttnIoArgs& a, cudaStream_t stream);
+
 // Assignment tail (lightglue.py:265-318) on projected descriptors p [S, Lp, 256] (already / 256^0.25)
 struct AssignArgs {
   const float* p;        // [S, Lp, 256]

@@ -425,6 +425,33 @@ class LightGlue(nn.Module):
             )
         return full, m0, m1, ms0, ms1
 
+    def attention(self, q0, k0, v0, q1, k1, v1, cross: bool = False):
+        """Kernel-level entry (``lg_attention``): ``Attention.forward`` (reference 97-137) on projected / rotated
+        heads ``[B, 4, M|N, 64]`` through the attention kernel of this matcher's precision mode.  Self
+        (``cross=False``): each image attends to itself; cross: image 0 queries image 1's keys / values and vice
+        versa (210-214).  Returns ``(ctx0 [B, M, 256], ctx1 [B, N, 256])`` fp32, heads concatenated h-major."""
+        device = q0.device
+        b, hh, m, dh = q0.shape
+        n = q1.shape[2]
+        assert hh == 4 and dh == 64 and k0.shape == q0.shape == v0.shape and k1.shape == q1.shape == v1.shape
+        with torch.cuda.device(device):
+            handle = self._get_handle(device)
+            lib = _cabi.load()
+            ws = self._workspace(handle, device, b, m, n)
+            ts = [t.detach().to(device=device, dtype=torch.float32).contiguous() for t in (q0, k0, v0, q1, k1, v1)]
+            c0 = torch.empty(b, m, 256, dtype=torch.float32, device=device)
+            c1 = torch.empty(b, n, 256, dtype=torch.float32, device=device)
+            if self.timing:
+                lib.lg_timing_enable(handle, 1)
+                self.timing = False
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _cabi.check(
+                lib.lg_attention(handle, b, m, n, int(bool(cross)), *[t.data_ptr() for t in ts], c0.data_ptr(), c1.data_ptr(),
+                                 ws.data_ptr(), ws.numel(), stream),
+                "lg_attention",
+            )
+        return c0, c1
+
     def kernel_times(self) -> dict:
         """Summed device milliseconds / launch counts per kernel class since timing was switched on."""
         if self._handle is None:
