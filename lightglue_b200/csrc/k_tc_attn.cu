@@ -336,6 +336,8 @@ constexpr int B_STAGE_BYTES = K_TILE_BYTES + B_V_TILE_BYTES;  // 16 KB
 
 template <bool FAST>
 __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_constant__ AttnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();  // the sequence lengths read right below belong to the dependency chain
   const int s = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * p.rows_per_cta;
   const int len_q = p.st.len[s];
   if (r0 >= len_q || lg_pair_stopped(p.st, s)) return;
@@ -715,9 +717,17 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
       if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
       attr2 = true;
     }
-    if (h->cfg.precision == LG_PREC_BF16) tc_attention2_kernel<true><<<grid, 384, smem2, stream>>>(p);
-    else tc_attention2_kernel<false><<<grid, 384, smem2, stream>>>(p);
-    LG_CHECK_LAUNCH();
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute at[1];
+    cfg.gridDim = grid; cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem2; cfg.stream = stream;
+    if (tc_use_pdl()) {
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+    }
+    const cudaError_t e = h->cfg.precision == LG_PREC_BF16 ? cudaLaunchKernelEx(&cfg, tc_attention2_kernel<true>, p)
+                                                          : cudaLaunchKernelEx(&cfg, tc_attention2_kernel<false>, p);
+    if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
     return 0;
   }
   constexpr int smem = 2 * Q_TILE_BYTES + KV_STAGES * KV_STAGE_BYTES + 1024 + 256;

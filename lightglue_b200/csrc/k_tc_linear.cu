@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
   const int total_tiles = n_tiles * p.st.S * (p.st.Lp / BM);
   const int iters = p.passes * p.kb_total;
 
+  pdl_launch_dependents();  // the next kernel's CTAs may take this SM as soon as this CTA has left it
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_hi[0]);
     tma_prefetch_desc(&p.w_hi);
@@ -208,6 +209,9 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
   if (MC) cluster_sync_all();  // the peer's barriers are initialised before anything can arrive on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barriers, TMEM, descriptor prefetch, LayerNorm vectors = weights) overlapped the tail of the
+  // previous kernel; activations, lengths and stop flags are only read from here on
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -792,13 +796,20 @@ int launch_linear_t(TcLinParams& p, int n_tiles, cudaStream_t stream) {
   const int total = n_tiles * p.st.S * (p.st.Lp / BM);
   int grid = total < g_num_sms ? total : g_num_sms;
   cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
+  unsigned na = 0;
   if (MC) {
     grid &= ~1;  // whole clusters of two (total is even: S is even)
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (tc_use_pdl()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(LinCfg<NSLOT>::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaError_t e = cudaLaunchKernelEx(&cfg, tc_linear_kernel<NSLOT, EPI, MC>, p);
   if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);

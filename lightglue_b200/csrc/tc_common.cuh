@@ -7,6 +7,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace tc {
 
@@ -172,6 +173,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+// Programmatic dependent launch (kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization):
+// `pdl_launch_dependents` lets the next kernel of the stream become resident as SMs drain, `pdl_wait` blocks until
+// every kernel this one depends on has completed and its memory is visible.  Nothing before `pdl_wait` may touch
+// global memory a predecessor writes; both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// host: launch attribute for such kernels (LG_NO_PDL=1 falls back to plain stream order)
+inline bool tc_use_pdl() {
+  static const bool on = !(getenv("LG_NO_PDL") && atoi(getenv("LG_NO_PDL")) != 0);
+  return on;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
