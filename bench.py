@@ -257,9 +257,40 @@ def main():
         print(json.dumps({"profile": True, "launches_per_step": matcher.last_launch_count()}))
         return
 
-    out = None
-    for _ in range(args.warmup):
-        out = step_resident()
+    def run_resident(n_steps, in_flight):
+        """n_steps forwards on resident inputs.  in_flight = 1: step i+1 is enqueued before step i's host-side result
+        (stop, per-pair match lists) is resolved, so the GPU never waits for the host; in_flight = 0: every forward is
+        resolved before the next is enqueued (the reference's calling pattern).  Either way every step's result is
+        resolved before the function returns.  N > 1: each step also gathers the match indices (int32 on the wire)."""
+        prev, last = None, None
+        for _ in range(n_steps):
+            cur = matcher.forward_async(resident)
+            if world > 1:
+                wire = cur.tensors["matches0"].to(torch.int32)
+                buf = [torch.empty_like(wire) for _ in range(world)]
+                dist.all_gather(buf, wire)
+            if in_flight == 0:
+                last = cur.result()
+                continue
+            if prev is not None:
+                last = prev.result()
+            prev = cur
+        return prev.result() if prev is not None else last
+
+    # warm-up: W steps in each host calling pattern (also absorbs their one-time allocations), timed to pick the
+    # pattern the timed region will use; all ranks must agree, so the verdict of rank 0 is broadcast
+    mode_ms = []
+    for mode in (0, 1):
+        run_resident(1, mode)
+        torch.cuda.synchronize(dev)
+        t0 = time.time()
+        out = run_resident(args.warmup, mode)
+        torch.cuda.synchronize(dev)
+        mode_ms.append((time.time() - t0) * 1e3 / args.warmup)
+    pick = torch.tensor([1 if mode_ms[1] <= mode_ms[0] else 0], device=dev)
+    if world > 1:
+        dist.broadcast(pick, src=0)
+    in_flight = int(pick.item())
     launches_per_step = matcher.last_launch_count()
 
     # ---- timed region 1: inputs resident in HBM (inputs 134 MB + multi-GB workspace: larger than the 126 MB L2)
@@ -271,12 +302,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     e0.record()
-    for _ in range(args.steps):
-        out = step_resident()
-        if world > 1:  # the final gather of the match indices (int32 on the wire)
-            wire = out["matches0"].to(torch.int32)
-            buf = [torch.empty_like(wire) for _ in range(world)]
-            dist.all_gather(buf, wire)
+    out = run_resident(args.steps, in_flight)
     e1.record()
     barrier()
     t_wall1 = time.time()
@@ -377,7 +403,10 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B, "keypoints": N_KPTS, "descriptor_dim": DESC,
                        "layers": LAYERS, "precision": args.precision, "parallelism": f"pairs sharded over {world} GPU(s)",
-                       "l2": "inputs (134 MB/step) + workspace (GBs) exceed the 126 MB L2; no explicit flush"},
+                       "l2": "inputs (134 MB/step) + workspace (GBs) exceed the 126 MB L2; no explicit flush",
+                       "host_pipelining": {"forwards_in_flight": in_flight, "warmup_ms_per_step_sync": mode_ms[0],
+                                           "warmup_ms_per_step_one_in_flight": mode_ms[1],
+                                           "note": "every step's stop / match lists are resolved inside the timed region"}},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,

@@ -130,6 +130,7 @@ class LightGlue(nn.Module):
         self._handle = None  # (C handle, device index, signature of the packed weights)
         self._ws: Dict[tuple, torch.Tensor] = {}
         self._graphs: Dict[tuple, tuple] = {}
+        self._meta_pool: Dict[int, list] = {}  # batch size -> free pinned [2, B] int32 read-back buffers
         self.timing = False
 
     # ------------------------------------------------------------------ weights
@@ -238,7 +239,16 @@ class LightGlue(nn.Module):
         return float(np.clip(0.8 + 0.1 * np.exp(-4.0 * layer_index / self.conf.n_layers), 0, 1))
 
     def forward(self, data: dict) -> dict:
-        """Match keypoints and descriptors between two images (reference 456-481).
+        """Match keypoints and descriptors between two images (reference 456-481): ``forward_async(data).result()``."""
+        return self.forward_async(data).result()
+
+    def forward_async(self, data: dict) -> "PendingMatch":
+        """Enqueue one forward on the current stream and return without waiting for the GPU.
+
+        The reference synchronises several times per layer; this path has a single host dependency -- the python
+        int ``stop`` and the lengths of the per-pair ``matches`` lists -- which ``PendingMatch.result()`` resolves
+        from a pinned read-back buffer.  Callers that keep one forward in flight while they post-process the
+        previous one (``lightglue_b200.pipeline.match_stream``, ``bench.py``) never leave the GPU idle.
 
         data = {"image0": {"keypoints" [B,M,2], "descriptors" [B,M,D], optional "image_size" [B,2],
         optional "scales"/"oris" [B,M]}, "image1": {...}}  ->  dict with matches0/1, matching_scores0/1,
@@ -358,8 +368,24 @@ class LightGlue(nn.Module):
                 io = {k: (None if v is None else v.clone()) for k, v in io.items()}  # results must not alias the graph's buffers
             m0, m1, ms0, ms1, meta = io["m0"], io["m1"], io["ms0"], io["ms1"], io["meta"]
             pr0, pr1, pairs, pscores = io["pr0"], io["pr1"], io["pairs"], io["pscores"]
-            meta_h = meta.cpu()  # the single device->host read-back: stop flags + match counts
+            # the single device->host read-back (stop flags + match counts), asynchronous into pinned memory
+            pool = self._meta_pool.get(b)
+            if pool is None:  # pinned allocation is slow and synchronises the device: take a few buffers at once
+                block = torch.empty(4, 2, b, dtype=torch.int32, pin_memory=True)
+                pool = self._meta_pool[b] = [block[i] for i in range(4)]
+            meta_h = pool.pop() if pool else torch.empty(2, b, dtype=torch.int32, pin_memory=True)
+            meta_h.copy_(meta, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(device))
+        return PendingMatch(self, done, meta_h, (b, m, n), prune, l0 is not None or l1 is not None,
+                            dict(m0=m0, m1=m1, ms0=ms0, ms1=ms1, pr0=pr0, pr1=pr1, pairs=pairs, pscores=pscores))
 
+    def _finish(self, meta_h, shape, prune, ragged, dev) -> dict:
+        """Assemble the reference's output dict once the read-back buffer is valid."""
+        b, m, n = shape
+        m0, m1, ms0, ms1 = dev["m0"], dev["m1"], dev["ms0"], dev["ms1"]
+        pr0, pr1, pairs, pscores = dev["pr0"], dev["pr1"], dev["pairs"], dev["pscores"]
+        device = m0.device
         stop = int(meta_h[0].max())
         if m == 0 or n == 0:  # reference 568-588: tensors instead of lists
             matches = torch.empty(b, 0, 2, dtype=torch.int64, device=device)
@@ -384,7 +410,7 @@ class LightGlue(nn.Module):
             "prune0": prune0,
             "prune1": prune1,
         }
-        if l0 is not None or l1 is not None:  # ragged batch: per-pair exit layers for split_outputs
+        if ragged:  # ragged batch: per-pair exit layers for split_outputs
             res["stops"] = [int(v) for v in meta_h[0].tolist()]
         return res
 
@@ -476,3 +502,30 @@ class LightGlue(nn.Module):
 
     def last_launch_count(self) -> int:
         return 0 if self._handle is None else int(_cabi.load().lg_last_launch_count(self._handle[0]))
+
+
+class PendingMatch:
+    """A forward that has been enqueued but whose host-side result (``stop``, list lengths) is not resolved yet.
+
+    ``tensors`` are the device outputs (valid in stream order right away); ``result()`` waits for the read-back of
+    the [stop | n_matches] words and returns the reference's output dict; it may be called more than once."""
+
+    def __init__(self, matcher, done, meta_h, shape, prune, ragged, dev):
+        self._matcher, self._done, self._meta, self._shape = matcher, done, meta_h, shape
+        self._prune, self._ragged, self._dev, self._res = prune, ragged, dev, None
+
+    @property
+    def tensors(self) -> dict:
+        d = self._dev
+        return {"matches0": d["m0"], "matches1": d["m1"], "matching_scores0": d["ms0"], "matching_scores1": d["ms1"]}
+
+    def done(self) -> bool:
+        return self._res is not None or self._done.query()
+
+    def result(self) -> dict:
+        if self._res is None:
+            self._done.synchronize()
+            self._res = self._matcher._finish(self._meta, self._shape, self._prune, self._ragged, self._dev)
+            self._matcher._meta_pool.setdefault(self._shape[0], []).append(self._meta)  # recycle the pinned buffer
+            self._meta = None
+        return self._res

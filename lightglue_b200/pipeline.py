@@ -1,9 +1,10 @@
 """Host-to-device pipelining for batched matching.
 
-``LightGlue.forward`` is asynchronous on the current stream except for its single D2H read-back, so
-the H2D copy of batch i+1 (pinned host memory, separate copy stream) can overlap the kernels of
-batch i.  ``match_stream`` does exactly that with two in-flight device staging slots; results come
-back in pinned host tensors.  This is the throughput path a server fed from host memory uses (the
+``LightGlue.forward_async`` enqueues a forward without waiting for the GPU (its only host dependency, the
+``stop`` / match-count words, is read back asynchronously), so the H2D copy of batch i+1 (pinned host
+memory, separate copy stream) overlaps the kernels of batch i and the kernels of batch i+1 are queued
+before batch i's result is handed out: the GPU never idles between batches.  Results come back in pinned
+host tensors.  This is the throughput path a server fed from host memory uses (the
 reference has no equivalent: its ``match_pair`` moves one pair at a time, utils.py:150-165).
 """
 from __future__ import annotations
@@ -58,7 +59,8 @@ def match_stream(matcher, batches: Iterable[dict], device: torch.device | None =
         for v in dev.values():
             for t in v.values():
                 t.record_stream(compute)
-        out = matcher(dev)
+        pend = matcher.forward_async(dev)  # queued behind the previous batch's kernels; no host wait
+        out = pend.tensors
         slot = slots[n_done % len(slots)]
         if not slot or any(slot[k].shape != out[k].shape for k in RESULT_KEYS):
             slot.clear()
@@ -69,11 +71,15 @@ def match_stream(matcher, batches: Iterable[dict], device: torch.device | None =
             host[k].copy_(out[k], non_blocking=True)
         done = torch.cuda.Event()
         done.record(compute)
-        host["stop"] = out["stop"]
         if pending is not None:
-            pending[1].synchronize()
-            yield pending[0]
-        pending = (host, done)
+            yield _resolve(pending)
+        pending = (host, done, pend)
     if pending is not None:
-        pending[1].synchronize()
-        yield pending[0]
+        yield _resolve(pending)
+
+
+def _resolve(pending):
+    host, done, pend = pending
+    done.synchronize()            # the result copies of that batch have landed in the pinned slot
+    host["stop"] = pend.result()["stop"]
+    return host
