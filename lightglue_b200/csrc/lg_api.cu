@@ -37,7 +37,9 @@ int lg_set_cuda_error(cudaError_t e, const char* file, int line) {
 
 extern "C" const char* lg_last_error(void) { return g_err; }
 extern "C" const char* lg_build_info(void) {
-  return "lightglue_b200 abi=1 arch=sm_100a (" __DATE__ " " __TIME__ ")";
+#define LG_STR2(x) #x
+#define LG_STR(x) LG_STR2(x)
+  return "lightglue_b200 abi=" LG_STR(LG_ABI_VERSION) " arch=sm_100a (" __DATE__ " " __TIME__ ")";
 }
 
 // ------------------------------------------------------------------------------------------------
