@@ -86,7 +86,9 @@ __global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_const
   const int nt = (len_q - r0 > QT) ? 2 : 1;  // live query tiles in this CTA
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // align by OFFSETTING the shared array (not by rebuilding a pointer from an integer): the compiler keeps the
+  // shared address space and emits LDS / STS instead of generic LD / ST for everything derived from it
+  uint8_t* smem = smem_raw + ((1024u - (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(smem_raw)) & 1023u)) & 1023u);
   uint8_t* sq = smem;                                  // 2 x 16 KB
   uint8_t* skvb = smem + 2 * Q_TILE_BYTES;             // KV_STAGES x 18 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(skvb + KV_STAGES * KV_STAGE_BYTES);
@@ -347,7 +349,9 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
   const int nt = (p.rows_per_cta > QT && len_q - r0 > QT) ? 2 : 1;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // align by OFFSETTING the shared array (not by rebuilding a pointer from an integer): the compiler keeps the
+  // shared address space and emits LDS / STS instead of generic LD / ST for everything derived from it
+  uint8_t* smem = smem_raw + ((1024u - (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(smem_raw)) & 1023u)) & 1023u);
   uint8_t* sq = smem;                                  // 2 x 16 KB
   uint8_t* skvb = smem + 2 * Q_TILE_BYTES;             // B_KV_STAGES x 16 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(skvb + B_KV_STAGES * B_STAGE_BYTES);
