@@ -15,6 +15,9 @@ EXPORTS = (
     "lg_last_launch_count", "lg_timing_enable", "lg_kernel_time_ms", "lg_last_error", "lg_build_info",
     "lg_debug_timeout_code",
 )
+# include/superpoint_b200.h (same library)
+SP_ABI_VERSION = 1
+SP_EXPORTS = ("sp_weight_blob_floats", "sp_create", "sp_destroy", "sp_max_keypoints", "sp_workspace_bytes", "sp_forward")
 
 
 class LgConfig(C.Structure):
@@ -22,6 +25,13 @@ class LgConfig(C.Structure):
         ("abi_version", C.c_int32), ("input_dim", C.c_int32), ("pos_dim", C.c_int32), ("n_layers", C.c_int32),
         ("precision", C.c_int32), ("depth_confidence", C.c_float), ("width_confidence", C.c_float),
         ("filter_threshold", C.c_float),
+    ]
+
+
+class SpConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("nms_radius", C.c_int32), ("max_num_keypoints", C.c_int32),
+        ("remove_borders", C.c_int32), ("detection_threshold", C.c_float),
     ]
 
 
@@ -79,6 +89,19 @@ def load():
     ]
     lib.lg_attention.restype = C.c_int
     lib.lg_attention.argtypes = [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 8 + [C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.sp_weight_blob_floats.restype = C.c_size_t
+    lib.sp_weight_blob_floats.argtypes = []
+    lib.sp_create.restype = C.c_int
+    lib.sp_create.argtypes = [C.POINTER(SpConfig), C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.sp_destroy.restype = C.c_int
+    lib.sp_destroy.argtypes = [C.c_void_p]
+    lib.sp_max_keypoints.restype = C.c_int64
+    lib.sp_max_keypoints.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    lib.sp_workspace_bytes.restype = C.c_size_t
+    lib.sp_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    lib.sp_forward.restype = C.c_int
+    lib.sp_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 5 + [
+        C.c_size_t, C.c_void_p]
     lib.lg_last_launch_count.restype = C.c_int64
     lib.lg_last_launch_count.argtypes = [C.c_void_p]
     lib.lg_timing_enable.restype = C.c_int
