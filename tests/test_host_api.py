@@ -77,8 +77,9 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
 
     src = tmp_path / "layout.c"
     src.write_text(
-        '#include <stdio.h>\n#include <stddef.h>\n#include "lightglue_b200.h"\n'
+        '#include <stdio.h>\n#include <stddef.h>\n#include "lightglue_b200.h"\n#include "superpoint_b200.h"\n'
         "int main(void) {\n"
+        '  printf("%zu %zu %d ", sizeof(SpConfig), offsetof(SpConfig, detection_threshold), SP_ABI_VERSION);\n'
         '  printf("%zu %zu %zu %zu %zu %zu %zu %d\\n", sizeof(LgConfig), sizeof(LgInputs), sizeof(LgOutputs),\n'
         "         offsetof(LgInputs, pruning_threshold), offsetof(LgInputs, lens0), offsetof(LgInputs, lens1),\n"
         "         offsetof(LgOutputs, log_assignment), LG_ABI_VERSION);\n"
@@ -88,6 +89,7 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [
+        C.sizeof(_cabi.SpConfig), _cabi.SpConfig.detection_threshold.offset, _cabi.SP_ABI_VERSION,
         C.sizeof(_cabi.LgConfig), C.sizeof(_cabi.LgInputs), C.sizeof(_cabi.LgOutputs),
         _cabi.LgInputs.pruning_threshold.offset, _cabi.LgInputs.lens0.offset, _cabi.LgInputs.lens1.offset,
         _cabi.LgOutputs.log_assignment.offset, _cabi.ABI_VERSION,
