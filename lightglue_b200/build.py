@@ -6,6 +6,7 @@ resulting .so travels to the GPU box with the repo snapshot.
 """
 from __future__ import annotations
 
+import fcntl
 import os
 import subprocess
 
@@ -25,16 +26,25 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library if it is missing or older than its sources; returns its path."""
-    if force or _stale():
-        jobs = str(min(8, os.cpu_count() or 1))
-        cmd = ["make", "-C", CSRC, "-j", jobs] + (["-B"] if force else [])
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if verbose or res.returncode != 0:
-            print(res.stdout[-4000:])
-            print(res.stderr[-8000:])
-        if res.returncode != 0:
-            raise RuntimeError("building liblightglue_b200.so failed (see output above)")
+    """Compile the CUDA library if it is missing or older than its sources; returns its path.  Serialised with a
+    file lock: the ranks of a torchrun job import the package at the same time and must not run `make` concurrently
+    (the first one builds, the others then find the library up to date)."""
+    if not (force or _stale()):
+        return LIB
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or _stale():
+                jobs = str(min(8, os.cpu_count() or 1))
+                cmd = ["make", "-C", CSRC, "-j", jobs] + (["-B"] if force else [])
+                res = subprocess.run(cmd, capture_output=True, text=True)
+                if verbose or res.returncode != 0:
+                    print(res.stdout[-4000:])
+                    print(res.stderr[-8000:])
+                if res.returncode != 0:
+                    raise RuntimeError("building liblightglue_b200.so failed (see output above)")
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
