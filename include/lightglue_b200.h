@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define LG_ABI_VERSION 2
+#define LG_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define LG_API __attribute__((visibility("default")))
@@ -144,6 +144,14 @@ LG_API int lg_assign(LgHandle* h, int32_t layer, int32_t B, int32_t M, int32_t N
 LG_API int lg_attention(LgHandle* h, int32_t B, int32_t M, int32_t N, int32_t cross, const float* q0, const float* k0,
                  const float* v0, const float* q1, const float* k1, const float* v1, float* ctx0, float* ctx1,
                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Block-level parity hook (per-layer comparison against the reference's hooks on
+ * `transformers[i]`, lightglue.py:541): while `buf` is non-NULL every lg_forward on this handle copies the fp32
+ * residual stream after each transformer layer i into buf[i][s][r][256], s < 2B sequences (image0 of pair s, then
+ * image1 of pair s - B), r < lg_padded_length(M, N) rows (rows past a sequence's length are unspecified; with point
+ * pruning rows are in the compacted order).  `floats` = capacity of buf; NULL switches the capture off. */
+LG_API int lg_debug_capture_layers(LgHandle* h, float* buf, size_t floats);
+LG_API int32_t lg_padded_length(int32_t M, int32_t N);
 
 /* Number of kernel launches issued by the last lg_forward / lg_assign on this handle. */
 LG_API int64_t lg_last_launch_count(const LgHandle* h);

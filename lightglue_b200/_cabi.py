@@ -8,12 +8,12 @@ from . import build as _build
 
 PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2}
 K_ATTENTION, K_LINEAR, K_ASSIGN, K_OTHER = 0, 1, 2, 3
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = (
     "lg_weight_blob_floats", "lg_create", "lg_destroy", "lg_workspace_bytes", "lg_forward", "lg_assign", "lg_attention",
     "lg_last_launch_count", "lg_timing_enable", "lg_kernel_time_ms", "lg_last_error", "lg_build_info",
-    "lg_debug_timeout_code",
+    "lg_debug_timeout_code", "lg_debug_capture_layers", "lg_padded_length",
 )
 # include/superpoint_b200.h (same library)
 SP_ABI_VERSION = 1
@@ -112,6 +112,10 @@ def load():
     lib.lg_debug_timeout_code.restype = C.c_uint32
     lib.lg_debug_timeout_code.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     lib.lg_build_info.restype = C.c_char_p
+    lib.lg_debug_capture_layers.restype = C.c_int
+    lib.lg_debug_capture_layers.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.lg_padded_length.restype = C.c_int32
+    lib.lg_padded_length.argtypes = [C.c_int32, C.c_int32]
     _lib = lib
     return lib
 

@@ -249,6 +249,11 @@ __global__ void __launch_bounds__(256) adapt_gather_kernel(GatherArgs a, SeqStat
   const int s = blockIdx.y;
   const int r = blockIdx.x * 8 + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && s < st.B) {
+    // pruning left one image of the pair without points: the reference breaks out at the top of the next layer
+    // (539-540) and answers from its empty branch (568-588) with stop = (layer + 1) + 1; nothing matches
+    if (a.stop_layer[s] == 0 && (a.len_out[s] == 0 || a.len_out[s + st.B] == 0)) a.stop_layer[s] = a.layer + 2;
+  }
   if (r >= a.len_in[s]) return;
   const int dst = a.pos[(long)s * st.Lp + r];
   if (dst < 0) return;

@@ -232,12 +232,7 @@ __global__ void __launch_bounds__(256) simt_attention_kernel(const float* __rest
 int simt_attention(const float* q, const float* k, const float* v, float* ctx, int kv_shift, const SeqState& st,
                    cudaStream_t stream) {
   const size_t smem = (2 * AT * ALD + AT * 64) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(simt_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
-    attr_set = true;
-  }
+  if (int r = lg_func_smem_once((const void*)simt_attention_kernel, (int)smem)) return r;
   dim3 grid(st.Lp / AT, LG_HEADS, st.S);
   simt_attention_kernel<<<grid, 256, smem, stream>>>(q, k, v, ctx, kv_shift, st);
   LG_CHECK_LAUNCH();

@@ -677,18 +677,13 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
   h->launches += 1;
   if (use_ref) {
     const size_t smem = (2 * AT * ALD + AT * 64) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(attn_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
-      attr_set = true;
-    }
+    if (int r = lg_func_smem_once((const void*)attn_ref_kernel, (int)smem)) return r;
     attn_ref_kernel<<<dim3(st.Lp / AT, LG_HEADS, st.S), 256, smem, stream>>>(b.q, kbuf, b.vt, b.ctxh, b.ctxl, kv_shift, st);
     LG_CHECK_LAUNCH();
     return 0;
   }
   // tensor maps depend only on (buffers, S, Lp): cache the last two sets (self: k = b.k, cross: k = b.q)
-  static thread_local AttnMapCache cache[2];
+  static thread_local AttnMapCache cache[2];  // keyed by buffer pointers: device addresses are unique per device (UVA)
   AttnMapCache* c = nullptr;
   for (auto& e : cache)
     if (e.q == b.q && e.k == kbuf && e.vt == b.vt && e.S == st.S && e.Lp == st.Lp) c = &e;
@@ -708,19 +703,13 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
   dim3 grid((st.Lp + 2 * QT - 1) / (2 * QT), LG_HEADS, st.S);
   p.rows_per_cta = 2 * QT;
   if (variant == 2) {
-    if ((long)grid.x * grid.y * grid.z < 2 * 148) {  // fewer CTAs than resident slots: one query tile per CTA instead
+    if ((long)grid.x * grid.y * grid.z < 2 * lg_num_sms()) {  // fewer CTAs than resident slots: one query tile per CTA instead
       p.rows_per_cta = QT;
       grid.x = st.Lp / QT;
     }
     constexpr int smem2 = 2 * Q_TILE_BYTES + B_KV_STAGES * B_STAGE_BYTES + 1024 + 256;
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaError_t e = cudaFuncSetAttribute(tc_attention2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(tc_attention2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-      if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
-      attr2 = true;
-    }
+    if (int r = lg_func_smem_once((const void*)tc_attention2_kernel<true>, smem2)) return r;
+    if (int r = lg_func_smem_once((const void*)tc_attention2_kernel<false>, smem2)) return r;
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute at[1];
     cfg.gridDim = grid; cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem2; cfg.stream = stream;
@@ -735,14 +724,8 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
     return 0;
   }
   constexpr int smem = 2 * Q_TILE_BYTES + KV_STAGES * KV_STAGE_BYTES + 1024 + 256;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
-    attr = true;
-  }
+  if (int r = lg_func_smem_once((const void*)tc_attention_kernel<true>, smem)) return r;
+  if (int r = lg_func_smem_once((const void*)tc_attention_kernel<false>, smem)) return r;
   if (h->cfg.precision == LG_PREC_BF16) tc_attention_kernel<true><<<grid, 384, smem, stream>>>(p);
   else tc_attention_kernel<false><<<grid, 384, smem, stream>>>(p);
   LG_CHECK_LAUNCH();

@@ -778,22 +778,11 @@ int omap_qk(LgHandle* h, CUtensorMap* out, const void* base, uint64_t Lp, uint64
   return 0;
 }
 
-int g_num_sms = 0;
 template <int NSLOT, int EPI, bool MC>
 int launch_linear_t(TcLinParams& p, int n_tiles, cudaStream_t stream) {
   constexpr int smem = LinCfg<NSLOT>::SMEM;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<NSLOT, EPI, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
-    if (g_num_sms <= 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-      if (g_num_sms <= 0) g_num_sms = 148;
-    }
-    attr = true;
-  }
+  if (int r = lg_func_smem_once((const void*)tc_linear_kernel<NSLOT, EPI, MC>, smem)) return r;
+  const int g_num_sms = lg_num_sms();
   p.n_tiles = n_tiles;
   const int total = n_tiles * p.st.S * (p.st.Lp / BM);
   int grid = total < g_num_sms ? total : g_num_sms;

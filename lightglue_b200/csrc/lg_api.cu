@@ -36,6 +36,40 @@ int lg_set_cuda_error(cudaError_t e, const char* file, int line) {
   } while (0)
 
 extern "C" const char* lg_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------------
+// per-device one-time setup
+// ------------------------------------------------------------------------------------------------
+#include <map>
+#include <mutex>
+namespace {
+std::mutex g_dev_mu;
+std::map<std::pair<int, const void*>, int> g_smem_done;  // (device, kernel) -> bytes opted in
+std::map<int, int> g_sms;
+}  // namespace
+int lg_func_smem_once(const void* func, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  auto it = g_smem_done.find({dev, func});
+  if (it != g_smem_done.end() && it->second >= bytes) return 0;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
+  g_smem_done[{dev, func}] = bytes;
+  return 0;
+}
+int lg_num_sms() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  auto it = g_sms.find(dev);
+  if (it != g_sms.end()) return it->second;
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  g_sms[dev] = n;
+  return n;
+}
 extern "C" const char* lg_build_info(void) {
 #define LG_STR2(x) #x
 #define LG_STR(x) LG_STR2(x)
@@ -84,9 +118,16 @@ extern "C" int lg_create(const LgConfig* cfg, const float* blob, size_t n_floats
   cudaStream_t stream = (cudaStream_t)stream_;
   LgHandle* h = new (std::nothrow) LgHandle();
   if (!h) return lg_set_error("lg_create: out of host memory");
+  struct Guard {  // every failure path below releases the handle and what it owns
+    LgHandle* h;
+    ~Guard() { if (h) lg_destroy(h); }
+  } guard{h};
+  h->wpk = nullptr;
+  memset(&h->tc, 0, sizeof(h->tc));
   h->cfg = *cfg;
   h->launches = 0;
   h->timing = false;
+  h->dbg_layers = nullptr; h->dbg_layers_floats = 0;
   for (int i = 0; i < LG_K_CLASSES; ++i) h->ev_used[i] = 0;
   CU(cudaGetDevice(&h->device));
   const int L = cfg->n_layers;
@@ -161,18 +202,18 @@ extern "C" int lg_create(const LgConfig* cfg, const float* blob, size_t n_floats
     t = t < 0 ? 0 : (t > 1 ? 1 : t);
     h->thr[i] = (float)t;
   }
-  memset(&h->tc, 0, sizeof(h->tc));
   if (cfg->precision != LG_PREC_FP32) {
     int r = tc_pack_weights(h, stream);
     if (r) return r;
   }
+  guard.h = nullptr;
   *out = h;
   return 0;
 }
 
 extern "C" int lg_destroy(LgHandle* h) {
   if (!h) return 0;
-  cudaFree(h->wpk);
+  if (h->wpk) cudaFree(h->wpk);
   tc_free_weights(&h->tc);
   for (int i = 0; i < LG_K_CLASSES; ++i)
     for (cudaEvent_t e : h->ev[i]) cudaEventDestroy(e);
@@ -183,6 +224,17 @@ extern "C" int lg_destroy(LgHandle* h) {
 extern "C" uint32_t lg_debug_timeout_code(LgHandle* h, uint32_t* words32) { return h ? tc_debug_timeout_code(h, words32) : 0; }
 
 extern "C" int64_t lg_last_launch_count(const LgHandle* h) { return h ? h->launches : 0; }
+
+extern "C" int lg_debug_capture_layers(LgHandle* h, float* buf, size_t floats) {
+  if (!h) return lg_set_error("null handle");
+  h->dbg_layers = buf;
+  h->dbg_layers_floats = buf ? floats : 0;
+  return 0;
+}
+extern "C" int32_t lg_padded_length(int32_t M, int32_t N) {
+  const int mx = M > N ? M : N;
+  return ((mx > 0 ? mx : 1) + LG_TILE - 1) / LG_TILE * LG_TILE;
+}
 
 extern "C" int lg_timing_enable(LgHandle* h, int32_t enable) {
   if (!h) return lg_set_error("null handle");
@@ -375,6 +427,7 @@ extern "C" int lg_forward(LgHandle* h, const LgInputs* in, const LgOutputs* out,
   h->launches = 0;
   const bool early = h->cfg.depth_confidence > 0, prune = h->cfg.width_confidence > 0;
   if (out->log_assignment && (early || prune)) return lg_set_error("lg_forward: log_assignment needs adaptivity off");
+  RC(check_outputs(out));
   if (M == 0 || N == 0) {  // lightglue.py:568-588: no keypoints -> nothing matched, stop = 1
     const long n0 = (long)B * M, n1 = (long)B * N;
     long mx = n0 > n1 ? n0 : n1;
@@ -386,7 +439,6 @@ extern "C" int lg_forward(LgHandle* h, const LgInputs* in, const LgOutputs* out,
     h->launches = 1;
     return 0;
   }
-  RC(check_outputs(out));
   if (!in->kpts0 || !in->kpts1 || !in->desc0 || !in->desc1) return lg_set_error("lg_forward: null input tensor");
   Workspace w;
   carve(h, B, M, N, (char*)workspace, &w);
@@ -467,6 +519,11 @@ extern "C" int lg_forward(LgHandle* h, const LgInputs* in, const LgOutputs* out,
         RC(tc_block(h, w.tc, st, i, blk, x, cs, stream));
       }
     }
+    if (h->dbg_layers) {
+      const size_t per = (size_t)2 * B * Lp * D;
+      if ((size_t)(i + 1) * per > h->dbg_layers_floats) return lg_set_error("lg_debug_capture_layers: buffer too small");
+      CU(cudaMemcpyAsync(h->dbg_layers + (size_t)i * per, x, per * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    }
     if (i == L - 1) break;  // no early stopping or adaptive width at the last layer (544-545)
     if (!early && !prune) continue;
     Timer t(h, LG_K_OTHER, stream);
@@ -485,7 +542,7 @@ extern "C" int lg_forward(LgHandle* h, const LgInputs* in, const LgOutputs* out,
     RC(misc_adapt_decide(a, st, stream));
     h->launches += 2;
     if (prune) {
-      GatherArgs ga{x, x_alt, cs, cs_alt, ind, ind_alt, w.prune, w.keep, w.pos, w.did_prune, len};
+      GatherArgs ga{x, x_alt, cs, cs_alt, ind, ind_alt, w.prune, w.keep, w.pos, w.did_prune, len, len_alt, w.stop_layer, i};
       RC(misc_adapt_gather(ga, st, stream));
       h->launches += 1;
       float* tf = x; x = x_alt; x_alt = tf;

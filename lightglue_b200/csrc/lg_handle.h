@@ -39,6 +39,7 @@ struct LgHandle {
   float thr[64];  // confidence_thresholds (lightglue.py:631-634)
   TcWeights tc;   // bf16 hi/lo copies for the tensor-core path (unused in fp32 mode)
   int64_t launches;
+  float* dbg_layers; size_t dbg_layers_floats;  // lg_debug_capture_layers
   bool timing;
   std::vector<cudaEvent_t> ev[LG_K_CLASSES];
   size_t ev_used[LG_K_CLASSES];

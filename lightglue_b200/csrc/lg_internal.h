@@ -20,6 +20,11 @@
 
 int lg_set_cuda_error(cudaError_t e, const char* file, int line);
 int lg_set_error(const char* msg);
+// Per-DEVICE one-time kernel setup (function attributes are per device: a process may drive several GPUs).
+// Opts `func` in to `bytes` of dynamic shared memory on the current device the first time it is seen there.
+int lg_func_smem_once(const void* func, int bytes);
+// SM count of the current device (queried once per device).
+int lg_num_sms();
 
 // Device-side view of the adaptive state; all arrays live in the workspace.
 struct SeqState {
@@ -101,6 +106,7 @@ struct GatherArgs {
   int* prune;                           // [S, Lp] by original index
   const unsigned char* keep; const int* pos; const int* did_prune;
   const int* len_in;
+  const int* len_out; int* stop_layer; int layer;  // an image pruned to 0 points ends its pair (lightglue.py:539-540)
 };
 int misc_adapt_gather(const GatherArgs& a, const SeqState& st, cudaStream_t stream);
 int misc_finalize_stop(int* stop_layer, int B, int n_layers, cudaStream_t stream);

@@ -478,6 +478,27 @@ class LightGlue(nn.Module):
             )
         return c0, c1
 
+    def forward_with_layers(self, data: dict):
+        """Debug / block-level parity (``lg_debug_capture_layers``): one forward that also returns the residual stream
+        after every transformer layer, ``[(desc0 [B, M, 256], desc1 [B, N, 256]), ...]`` -- what a forward hook on the
+        reference's ``transformers[i]`` sees (lightglue.py:541).  Dense, non-pruned batches only."""
+        k0, k1 = data["image0"]["keypoints"], data["image1"]["keypoints"]
+        b, m, n = k0.shape[0], k0.shape[1], k1.shape[1]
+        device = k0.device
+        lib = _cabi.load()
+        with torch.cuda.device(device):
+            handle = self._get_handle(device)
+            lp = int(lib.lg_padded_length(m, n))
+            buf = torch.zeros(self.conf.n_layers, 2 * b, lp, DIM, dtype=torch.float32, device=device)
+            _cabi.check(lib.lg_debug_capture_layers(handle, buf.data_ptr(), buf.numel()), "lg_debug_capture_layers")
+            try:
+                out = self.forward(data)
+                torch.cuda.synchronize(device)
+            finally:
+                lib.lg_debug_capture_layers(handle, None, 0)
+        layers = [(buf[i, :b, :m].clone(), buf[i, b:, :n].clone()) for i in range(int(out["stop"]))]
+        return out, layers
+
     def kernel_times(self) -> dict:
         """Summed device milliseconds / launch counts per kernel class since timing was switched on."""
         if self._handle is None:

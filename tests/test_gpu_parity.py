@@ -147,6 +147,109 @@ def test_tc_adaptive_runs_and_agrees(prec):
         assert diff <= (4 if prec == "bf16x3" else 40)
 
 
+TC_ADAPTIVE_CASES = ["adaptive_n512", "adaptive_n1200_th1024", "depth_only_n512", "width_only_n512"]
+
+
+@pytest.mark.parametrize("name", TC_ADAPTIVE_CASES)
+def test_index_exact_tc_modes_adaptive_identical_decisions(name):
+    """Every adaptive fixture on the index-exact tensor-core path: identical stop layer, identical prune counters,
+    identical match indices (no +-1, no allowance)."""
+    fix, data, sd = load_case(name)
+    gold = fix["out"]
+    out = build(fix, sd, "bf16x3")(to_cuda(data))
+    assert int(out["stop"]) == int(gold["stop"])
+    assert torch.equal(out["prune0"].cpu().double(), gold["prune0"].double())
+    assert torch.equal(out["prune1"].cpu().double(), gold["prune1"].double())
+    compare_outputs(out, gold, score_tol=1e-3)
+
+
+def test_index_exact_adaptive_n2048_default_flash_threshold():
+    """BASELINE config 3 (N=2048, depth 0.95 / width 0.99, pruning threshold 1536) on the index-exact tensor-core path
+    against the oracle: identical stop, prune counters and match indices."""
+    sd = synth.make_state_dict(adaptive=True)
+    data, _ = synth.make_pair(2048, b=1, seed=41)
+    ref = oracle.forward(sd, data, depth_confidence=0.95, width_confidence=0.99, pruning_threshold=1536)
+    m = LightGlue(features=None, precision="bf16x3")
+    m.load_state_dict(sd, strict=False)
+    out = m.cuda()(to_cuda(data))
+    assert int(out["stop"]) == int(ref["stop"])
+    assert torch.equal(out["prune0"].cpu(), ref["prune0"]) and torch.equal(out["prune1"].cpu(), ref["prune1"])
+    assert torch.equal(out["matches0"].cpu(), ref["matches0"]) and torch.equal(out["matches1"].cpu(), ref["matches1"])
+    assert float((out["matching_scores0"].cpu() - ref["matching_scores0"]).abs().max()) < 1e-3
+
+
+def test_index_exact_batched_b32_equals_single_n2048():
+    """BASELINE config 2 shape (B=32, N=2048) on the index-exact tensor-core path: every pair of the batch gives the
+    result of its own B=1 call (bit-identical indices and scores: the kernels never mix pairs)."""
+    sd = synth.make_state_dict()
+    m = LightGlue(features=None, precision="bf16x3", depth_confidence=-1, width_confidence=-1)
+    m.load_state_dict(sd, strict=False)
+    m = m.cuda()
+    data, _ = synth.make_pair(2048, b=32, seed=777)
+    cd = to_cuda(data)
+    out = m(cd)
+    for b in (0, 13, 31):
+        one = {k: {kk: vv[b : b + 1].contiguous() for kk, vv in v.items()} for k, v in cd.items()}
+        o1 = m(one)
+        assert torch.equal(o1["matches0"][0], out["matches0"][b]) and torch.equal(o1["matches1"][0], out["matches1"][b])
+        assert float((o1["matching_scores0"][0] - out["matching_scores0"][b]).abs().max()) <= 1e-6
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-4), ("bf16x3", 2e-3)])
+def test_per_layer_residual_stream_against_oracle(prec, tol):
+    """Block-level parity: the residual stream after every transformer layer (what a forward hook on the
+    reference's transformers[i] sees, lightglue.py:541) against the oracle's, through lg_debug_capture_layers."""
+    fix, data, sd = load_case("c1_n512")
+    ref = oracle.forward(sd, data, return_layers=True)
+    m = build(fix, sd, prec)
+    out, layers = m.forward_with_layers(to_cuda(data))
+    assert len(layers) == len(ref["layers"]) == 9
+    worst = 0.0
+    for i, ((a0, a1), (r0, r1)) in enumerate(zip(layers, ref["layers"])):
+        scale = max(float(r0.abs().max()), 1.0)
+        d = max(float((a0.cpu() - r0).abs().max()), float((a1.cpu() - r1).abs().max())) / scale
+        worst = max(worst, d)
+        assert d <= tol, f"layer {i}: relative deviation {d:.2e} > {tol}"
+    print(f"[{prec}] per-layer max relative deviation {worst:.2e}")
+
+
+def test_pruned_to_zero_points_ends_the_pair_like_the_reference():
+    """Pruning that leaves an image without points: the reference breaks at the top of the next layer and answers from
+    its empty branch (lightglue.py:539-540, 568-588): nothing matched, stop = that layer + 1."""
+    sd = synth.make_state_dict(adaptive=True)
+    for k in list(sd):  # matchability far below any threshold: every point is pruned at the first opportunity
+        if "matchability.bias" in k:
+            sd[k] = sd[k] - 200.0
+    data, _ = synth.make_pair(300, b=1, seed=91)
+    ref = oracle.forward(sd, data, depth_confidence=-1, width_confidence=0.99, pruning_threshold=-1)
+    assert int((ref["matches0"] > -1).sum()) == 0
+    for prec in ("fp32", "bf16x3"):
+        m = LightGlue(features=None, precision=prec, depth_confidence=-1, width_confidence=0.99)
+        m.load_state_dict(sd, strict=False)
+        m = m.cuda()
+        m.pruning_keypoint_thresholds = dict(LightGlue.pruning_keypoint_thresholds, flash=-1)
+        out = m(to_cuda(data))
+        assert int(out["stop"]) == int(ref["stop"]), (prec, out["stop"], ref["stop"])
+        assert bool((out["matches0"] == -1).all()) and bool((out["matches1"] == -1).all())
+        assert float(out["matching_scores0"].abs().max()) == 0.0
+        assert torch.equal(out["prune0"].cpu(), ref["prune0"]) and torch.equal(out["prune1"].cpu(), ref["prune1"])
+
+
+def test_two_devices_in_one_process():
+    """Per-device kernel setup (shared-memory opt-in, SM count): a second matcher on another GPU of the same process."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    fix, data, sd = load_case("c1_n512")
+    outs = []
+    for dev in (0, 1):
+        m = LightGlue(features=None, precision="bf16x3", depth_confidence=-1, width_confidence=-1)
+        m.load_state_dict(sd, strict=False)
+        m = m.eval().to(f"cuda:{dev}")
+        outs.append(m({k: {kk: vv.to(f"cuda:{dev}") for kk, vv in v.items()} for k, v in data.items()}))
+    assert torch.equal(outs[0]["matches0"].cpu(), outs[1]["matches0"].cpu())
+    compare_outputs(outs[1], fix["out"], score_tol=1e-3)
+
+
 def test_match_stream_equals_direct_forward():
     """The pinned-host streaming API (H2D one batch ahead on a copy stream) returns what forward returns."""
     from lightglue_b200.pipeline import match_stream

@@ -1,8 +1,6 @@
 """Pairs far below one 128-row tile through the tensor-core path against the oracle.
 
-Kept in a file that sorts after every other GPU test: it was added after the round's GPU budget was spent, so its
-first execution happens at round end -- a failure (or a poisoned CUDA context) here cannot disturb the suites that
-were validated.  Non-strict xfail until its first green run."""
+Green on the B200 since round 1's closing run (GPUTEST_r01.json)."""
 import pytest
 import torch
 
@@ -16,7 +14,6 @@ def to_cuda(data):
     return {k: {kk: vv.cuda() for kk, vv in v.items()} for k, v in data.items()}
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: first execution happens at round end")
 @pytest.mark.parametrize("m,n", [(5, 3), (1, 1), (130, 2), (127, 129)])
 def test_tiny_pairs_on_the_tensor_core_path(m, n):
     """Pairs far below one 128-row tile (Lp = 128 / 256) through the bf16x3 path against the oracle."""
