@@ -159,7 +159,9 @@ LG_API int64_t lg_last_launch_count(const LgHandle* h);
 /* Timing hooks for bench.py: lg_forward records a CUDA-event pair around every launch of the
  * named kernel class when enabled; lg_kernel_time_ms returns the summed milliseconds and launch
  * count since the last reset (synchronises on those events only). */
-enum { LG_K_ATTENTION = 0, LG_K_LINEAR = 1, LG_K_ASSIGN = 2, LG_K_OTHER = 3, LG_K_ASSIGN_MATRIX = 4, LG_K_CLASSES = 5 };
+enum { LG_K_ATTENTION = 0, LG_K_LINEAR = 1, LG_K_ASSIGN = 2, LG_K_OTHER = 3, LG_K_ASSIGN_MATRIX = 4,
+       /* sub-classes of LG_K_LINEAR (tensor-core modes): */ LG_K_QKV = 5, LG_K_FFN0 = 6, LG_K_FFN3 = 7,
+       /* whole materialising assignment stage (final_proj + sweeps + dustbin) */ LG_K_ASSIGN_STAGE = 8, LG_K_CLASSES = 9 };
 LG_API int lg_timing_enable(LgHandle* h, int32_t enable);
 LG_API int lg_kernel_time_ms(LgHandle* h, int32_t kernel_class, double* ms, int64_t* launches);
 

@@ -33,7 +33,7 @@ enum { TEPI_QKV = 0, TEPI_BF16 = 1, TEPI_LN_GELU = 2, TEPI_RESID = 3, TEPI_F32 =
 struct TcLinParams {
   CUtensorMap a_hi[2], a_lo[2];  // A segment 0 / 1
   CUtensorMap w_hi, w_lo;        // 3-D: (K, Nout, select), box 64 x 256 rows
-  CUtensorMap w_hi_half, w_lo_half;  // same tensors, box 64 x 128 rows: each CTA of a pair loads one half and multicasts it
+  CUtensorMap w_hi_half, w_lo_half;  // same tensors, box 64 x 128 rows: each CTA of a pair holds one half of the N tile (cta_group::2)
   int kb0, kb_total, passes, n_tiles;
   int epi, rope;
   SeqState st;
@@ -68,16 +68,26 @@ struct TcLinParams {
 // x 16 B per row) -> coalesced global loads / stores.
 // ------------------------------------------------------------------------------------------------
 
-template <int NSLOT>
+// CG2: CTA pairs (cta_group::2).  The two CTAs of a cluster take the two row tiles of a "tile pair" with the same
+// n-tile; one thread of the leader CTA issues M=256 MMAs that read A (128 rows) and HALF of the W tile (128 of its
+// 256 rows) from each CTA's shared memory, so every SM receives only half of the weight bytes, a ring stage is
+// 32 KB instead of 48 and more stages fit.  X3 (CG2 only): split-bf16 with the K block outermost -- one stage holds
+// A_hi, A_lo, W_hi, W_lo of a 64-wide K block and feeds all three passes (A_lo W_hi, A_hi W_lo, A_hi W_hi): the
+// W_hi / A_hi tiles are loaded once instead of twice.  With two accumulator slots (LayerNorm variant) the slots
+// take consecutive stages of the same format.  Non-CG2 (per-tile weight selection: final_proj heads, assignment
+// sweeps): one CTA per tile, passes outermost, as in round 1.
+template <int NSLOT, bool CG2, bool X3>
 struct LinCfg {
-  static constexpr int STAGES = 2;
+  static_assert(CG2 || !X3, "the K-outer split staging exists in the CTA-pair kernels only");
   static constexpr int NBUF = NSLOT == 1 ? 2 : 1;
   // epilogue warps: 8 (two per TMEM lane quarter, 128 columns each); the LayerNorm variant (512 columns, the
   // instruction-heaviest epilogue) runs 16 so that four warps per scheduler hide its latencies
   static constexpr int EW = NSLOT == 1 ? 8 : 16;
   static constexpr int GROUPS = EW / 4;
   static constexpr int THREADS = 64 + EW * 32;
-  static constexpr int STAGE_BYTES = A_TILE_BYTES + NSLOT * W_TILE_BYTES;
+  static constexpr int W_PART = CG2 ? W_TILE_BYTES / 2 : W_TILE_BYTES;  // bytes of one W tile held by this CTA
+  static constexpr int STAGE_BYTES = CG2 ? (X3 ? 2 * A_TILE_BYTES + 2 * W_PART : A_TILE_BYTES + W_PART)
+                                         : A_TILE_BYTES + NSLOT * W_TILE_BYTES;
   static constexpr int COLS = NSLOT * BN;
   // per epilogue warp: box A (4 KB: fp32 32x32 output box / rotary cos), box B (4 KB: 16-bit 32x64 box, hi or
   // fp16), box C (4 KB: rotary sin, or the dense 32x32 bf16 "lo" box).  The LayerNorm variant has no box A.
@@ -85,9 +95,14 @@ struct LinCfg {
   static constexpr int WARP_BYTES = NSLOT == 1 ? 3 * 4096 : 2048;
   static constexpr int BOXB_OFF = NSLOT == 1 ? 4096 : 0;
   static constexpr int BOXC_OFF = NSLOT == 1 ? 8192 : 0;
-  static constexpr int VEC_BYTES = 3 * COLS * 4;            // bias | ln gamma | ln beta
-  static constexpr int LNP_BYTES = 128 * GROUPS * 8;        // LayerNorm partial (mean, M2) per row per column group
-  static constexpr int SMEM = STAGES * STAGE_BYTES + EW * WARP_BYTES + VEC_BYTES + LNP_BYTES + 512 + 1024;
+  static constexpr int VEC_BYTES = (NSLOT == 1 ? 1 : 3) * COLS * 4;     // bias (| ln gamma | ln beta)
+  static constexpr int LNP_BYTES = NSLOT == 1 ? 0 : 128 * GROUPS * 8;    // LayerNorm partial (mean, M2) per row per column group
+  static constexpr int FIXED_BYTES = EW * WARP_BYTES + VEC_BYTES + LNP_BYTES + 512 + 1024;
+  static constexpr int SMEM_MAX = 232448;  // 227 KB per CTA
+  static constexpr int FIT = (SMEM_MAX - FIXED_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = FIT > 6 ? 6 : FIT;
+  static_assert(STAGES >= 2, "the TMA ring needs at least two stages");
+  static constexpr int SMEM = STAGES * STAGE_BYTES + FIXED_BYTES;
 };
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -128,9 +143,8 @@ __device__ __forceinline__ bool decode_tile(const TcLinParams& p, int t, int n_t
   return live;
 }
 
-// Tile schedule.  Plain mode: CTA c walks tiles c, c + grid, ...  Cluster mode (MC): the two CTAs of a cluster
-// take the two row tiles of a "tile pair" with the same n-tile, so that they consume the same W tiles and each
-// loads half of every W tile, multicast to both (halves the L2 -> SM weight traffic, which bounds these GEMMs).
+// Tile schedule.  Plain mode: CTA c walks tiles c, c + grid, ...  Pair mode (MC == CG2): the two CTAs of a cluster
+// take the two row tiles of a "tile pair" with the same n-tile; both walk the same list.
 template <bool MC>
 struct TileWalk {
   int cur, step, end, rank, n_tiles;
@@ -166,9 +180,10 @@ struct TileWalk {
   }
 };
 
-template <int NSLOT, int EPI, bool MC>
-__global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(const __grid_constant__ TcLinParams p) {
-  using C = LinCfg<NSLOT>;
+template <int NSLOT, int EPI, bool CG2, bool X3>
+__global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_kernel(const __grid_constant__ TcLinParams p) {
+  using C = LinCfg<NSLOT, CG2, X3>;
+  constexpr bool MC = CG2;
   constexpr int EPI_WARPS = C::EW;
   auto epi_bar = [] { epi_bar_n<C::EW * 32>(); };
   constexpr int STAGES = C::STAGES, NBUF = C::NBUF, STAGE_BYTES = C::STAGE_BYTES, COLS = C::COLS;
@@ -178,9 +193,9 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
   uint8_t* smem = smem_raw + ((1024u - (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(smem_raw)) & 1023u)) & 1023u);
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;  // 1024-aligned: per-warp TMA boxes
   float* s_bias = reinterpret_cast<float*>(epi_smem + EPI_WARPS * C::WARP_BYTES);
-  float* s_gamma = s_bias + COLS;
-  float* s_beta = s_gamma + COLS;
-  float2* s_lnp = reinterpret_cast<float2*>(s_beta + COLS);  // [GROUPS][128 rows]
+  float* s_gamma = s_bias + (NSLOT == 1 ? 0 : COLS);       // LayerNorm variant only
+  float* s_beta = s_gamma + (NSLOT == 1 ? 0 : COLS);
+  float2* s_lnp = reinterpret_cast<float2*>(s_bias + C::VEC_BYTES / 4);  // [GROUPS][128 rows]
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_lnp) + C::LNP_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
@@ -191,18 +206,27 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int n_tiles = p.n_tiles;
   const int total_tiles = n_tiles * p.st.S * (p.st.Lp / BM);
-  const int iters = p.passes * p.kb_total;
+  // ring iterations per tile: pair mode = (K block, accumulator slot), split-bf16 passes inside an iteration;
+  // plain mode = (pass, K block), all slots inside an iteration
+  const int iters = CG2 ? p.kb_total * NSLOT : p.passes * p.kb_total;
+  const int rank = CG2 ? (int)cluster_ctarank() : 0;
 
   pdl_launch_dependents();  // the next kernel's CTAs may take this SM as soon as this CTA has left it
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_hi[0]);
     tma_prefetch_desc(&p.w_hi);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], MC ? 2 : 1); }
-    for (int i = 0; i < NBUF; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
+    // pair mode: only the leader's `full` / `acc_empty` barriers are waited on (its TMA bytes AND the peer's complete
+    // there; both CTAs' epilogue warps arrive there); `empty` / `acc_full` exist in both CTAs and receive the leader's
+    // multicast commits
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NBUF; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], (CG2 ? 2 : 1) * EPI_WARPS); }
     for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&ldbar[i], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if (CG2) tmem_alloc_cg2<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   if (EPI == TEPI_LN_GELU && warp >= 2) {
     for (int i = threadIdx.x - 64; i < COLS; i += EPI_WARPS * 32) { s_gamma[i] = p.ln_g[i]; s_beta[i] = p.ln_b[i]; }
   }
@@ -226,22 +250,35 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
         for (int it = 0; it < iters; ++it, ++g) {
           const int stage = g % STAGES, round = g / STAGES;
           mbar_wait(&empty[stage], (round & 1) ^ 1, p.dbg, 17, it);
-          const int pass = it / p.kb_total, kb = it % p.kb_total;
-          // pass order (x3): A_lo*W_hi, A_hi*W_lo, A_hi*W_hi ; (bf16): A_hi*W_hi
-          const bool a_lo = (p.passes == 3) && pass == 0;
-          const bool w_lo = (p.passes == 3) && pass == 1;
-          const int seg = kb >= p.kb0 ? 1 : 0;
-          const int kc = (seg ? kb - p.kb0 : kb) * BK;
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-          tma_load_2d(sa, a_lo ? &p.a_lo[seg] : &p.a_hi[seg], kc, (int)ti.grow0, &full[stage]);
+          if (CG2) {
+            // pair mode: this CTA's A rows and its half (128 of 256 rows) of the W tile; the bytes of BOTH CTAs complete
+            // on the leader's barrier, which only the leader arms
+            const int kb = it / NSLOT, sl_ = it % NSLOT;
+            const int seg = kb >= p.kb0 ? 1 : 0;
+            const int kc = (seg ? kb - p.kb0 : kb) * BK;
+            const int wrow = (ti.n_tile * NSLOT + sl_) * BN + rank * (BN / 2);
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+            if (X3) {
+              tma_load_2d_cg2(sa, &p.a_hi[seg], kc, (int)ti.grow0, &full[stage]);
+              tma_load_2d_cg2(sa + A_TILE_BYTES, &p.a_lo[seg], kc, (int)ti.grow0, &full[stage]);
+              tma_load_3d_cg2(sa + 2 * A_TILE_BYTES, &p.w_hi_half, kb * BK, wrow, 0, &full[stage]);
+              tma_load_3d_cg2(sa + 2 * A_TILE_BYTES + C::W_PART, &p.w_lo_half, kb * BK, wrow, 0, &full[stage]);
+            } else {
+              tma_load_2d_cg2(sa, &p.a_hi[seg], kc, (int)ti.grow0, &full[stage]);
+              tma_load_3d_cg2(sa + A_TILE_BYTES, &p.w_hi_half, kb * BK, wrow, 0, &full[stage]);
+            }
+          } else {
+            const int pass = it / p.kb_total, kb = it % p.kb_total;
+            // pass order (x3): A_lo*W_hi, A_hi*W_lo, A_hi*W_hi ; (bf16): A_hi*W_hi
+            const bool a_lo = (p.passes == 3) && pass == 0;
+            const bool w_lo = (p.passes == 3) && pass == 1;
+            const int seg = kb >= p.kb0 ? 1 : 0;
+            const int kc = (seg ? kb - p.kb0 : kb) * BK;
+            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+            tma_load_2d(sa, a_lo ? &p.a_lo[seg] : &p.a_hi[seg], kc, (int)ti.grow0, &full[stage]);
 #pragma unroll
-          for (int sl_ = 0; sl_ < NSLOT; ++sl_) {
-            if (MC)  // this CTA's half (128 rows) of the W tile, delivered to both CTAs of the pair
-              tma_load_3d_mc(sa + A_TILE_BYTES + sl_ * W_TILE_BYTES + walk.rank * (W_TILE_BYTES / 2),
-                             w_lo ? &p.w_lo_half : &p.w_hi_half, kb * BK, (ti.n_tile * NSLOT + sl_) * BN + walk.rank * (BN / 2),
-                             0, &full[stage], (uint16_t)3);
-            else
+            for (int sl_ = 0; sl_ < NSLOT; ++sl_)
               tma_load_3d(sa + A_TILE_BYTES + sl_ * W_TILE_BYTES, w_lo ? &p.w_lo : &p.w_hi, kb * BK,
                           (ti.n_tile * NSLOT + sl_) * BN, ti.sel, &full[stage]);
           }
@@ -250,14 +287,16 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc(BM, BN, true);
+    constexpr uint32_t idesc = make_idesc(CG2 ? 2 * BM : BM, BN, true);
     int g = 0, li = 0;  // li: index among this CTA's live tiles
     TileWalk<MC> walk(total_tiles, n_tiles);
     TileInfo ti;
     bool store;
-    while (walk.next(p, ti, store)) {
+    while ((!CG2 || rank == 0) && walk.next(p, ti, store)) {  // pair mode: the leader issues for both CTAs
       const int buf = li % NBUF;
-      mbar_wait(&acc_empty[buf], ((li / NBUF) & 1) ^ 1, p.dbg, 20, li);  // epilogue has drained this accumulator
+      // the epilogue warps (pair mode: of both CTAs) have drained this accumulator
+      if (CG2) mbar_wait_cluster(&acc_empty[buf], ((li / NBUF) & 1) ^ 1, p.dbg, 20, li);
+      else mbar_wait(&acc_empty[buf], ((li / NBUF) & 1) ^ 1, p.dbg, 20, li);
       tc_fence_after();
       const uint32_t acc = tmem_base + buf * BN;
       for (int it = 0; it < iters; ++it, ++g) {
@@ -266,17 +305,37 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t adesc = make_sdesc_sw128(sa);
+          if (CG2) {
+            const int kb = it / NSLOT, sl_ = it % NSLOT;
+            const uint32_t d = acc + sl_ * BN;
+            if (X3) {
+              const uint64_t ahi = make_sdesc_sw128(sa), alo = make_sdesc_sw128(sa + A_TILE_BYTES);
+              const uint64_t whi = make_sdesc_sw128(sa + 2 * A_TILE_BYTES), wlo = make_sdesc_sw128(sa + 2 * A_TILE_BYTES + C::W_PART);
 #pragma unroll
-          for (int sl_ = 0; sl_ < NSLOT; ++sl_) {
-            const uint64_t bdesc = make_sdesc_sw128(sa + A_TILE_BYTES + sl_ * W_TILE_BYTES);
+              for (int k = 0; k < BK / 16; ++k) mma_ss_cg2(d, alo + 2 * k, whi + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              mma_ss(acc + sl_ * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) mma_ss_cg2(d, ahi + 2 * k, wlo + 2 * k, idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) mma_ss_cg2(d, ahi + 2 * k, whi + 2 * k, idesc, 1u);
+            } else {
+              const uint64_t adesc = make_sdesc_sw128(sa), bdesc = make_sdesc_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) mma_ss_cg2(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            mma_commit_cg2(&empty[stage], (uint16_t)3);  // frees the stage in both CTAs
+            if (it == iters - 1) mma_commit_cg2(&acc_full[buf], (uint16_t)3);
+          } else {
+            const uint64_t adesc = make_sdesc_sw128(sa);
+#pragma unroll
+            for (int sl_ = 0; sl_ < NSLOT; ++sl_) {
+              const uint64_t bdesc = make_sdesc_sw128(sa + A_TILE_BYTES + sl_ * W_TILE_BYTES);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                mma_ss(acc + sl_ * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
+            mma_commit(&empty[stage]);
+            if (it == iters - 1) mma_commit(&acc_full[buf]);
           }
-          if (MC) mma_commit_mc(&empty[stage], (uint16_t)3);  // the stage is shared: both CTAs must have consumed it
-          else mma_commit(&empty[stage]);
-          if (it == iters - 1) mma_commit(&acc_full[buf]);
         }
         __syncwarp();
       }
@@ -314,7 +373,7 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (lane == 0) { if (CG2) mbar_arrive_leader(&acc_empty[buf]); else mbar_arrive(&acc_empty[buf]); }
         ++li;
         continue;
       }
@@ -622,15 +681,18 @@ __global__ void __launch_bounds__(LinCfg<NSLOT>::THREADS, 1) tc_linear_kernel(co
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) { if (CG2) mbar_arrive_leader(&acc_empty[buf]); else mbar_arrive(&acc_empty[buf]); }
       ++li;
     }
     if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it / arrive on its barriers
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (MC) cluster_sync_all();  // no CTA leaves while the leader may still read its operands / arrive on its barriers
+  if (warp == 1) {
+    if (CG2) tmem_dealloc_cg2<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // fp32 -> bf16 hi (/ lo) for rows < len
@@ -778,18 +840,19 @@ int omap_qk(LgHandle* h, CUtensorMap* out, const void* base, uint64_t Lp, uint64
   return 0;
 }
 
-template <int NSLOT, int EPI, bool MC>
+template <int NSLOT, int EPI, bool CG2, bool X3>
 int launch_linear_t(TcLinParams& p, int n_tiles, cudaStream_t stream) {
-  constexpr int smem = LinCfg<NSLOT>::SMEM;
-  if (int r = lg_func_smem_once((const void*)tc_linear_kernel<NSLOT, EPI, MC>, smem)) return r;
-  const int g_num_sms = lg_num_sms();
+  using C = LinCfg<NSLOT, CG2, X3>;
+  constexpr int smem = C::SMEM;
+  if (int r = lg_func_smem_once((const void*)tc_linear_kernel<NSLOT, EPI, CG2, X3>, smem)) return r;
+  const int num_sms = lg_num_sms();
   p.n_tiles = n_tiles;
   const int total = n_tiles * p.st.S * (p.st.Lp / BM);
-  int grid = total < g_num_sms ? total : g_num_sms;
+  int grid = total < num_sms ? total : num_sms;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute at[2];
   unsigned na = 0;
-  if (MC) {
+  if (CG2) {
     grid &= ~1;  // whole clusters of two (total is even: S is even)
     at[na].id = cudaLaunchAttributeClusterDimension;
     at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
@@ -801,22 +864,28 @@ int launch_linear_t(TcLinParams& p, int n_tiles, cudaStream_t stream) {
     ++na;
   }
   cfg.attrs = at; cfg.numAttrs = na;
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(LinCfg<NSLOT>::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_linear_kernel<NSLOT, EPI, MC>, p);
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_linear_kernel<NSLOT, EPI, CG2, X3>, p);
   if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
   return 0;
 }
+template <int NSLOT, int EPI>
+int launch_linear_e(TcLinParams& p, int n_tiles, bool cg2, cudaStream_t stream) {
+  if (!cg2) return launch_linear_t<NSLOT, EPI, false, false>(p, n_tiles, stream);
+  return p.passes == 3 ? launch_linear_t<NSLOT, EPI, true, true>(p, n_tiles, stream)
+                       : launch_linear_t<NSLOT, EPI, true, false>(p, n_tiles, stream);
+}
 int launch_linear(TcLinParams& p, int n_tiles, cudaStream_t stream) {
-  static const bool use_mc = !(getenv("LG_TC_NO_MULTICAST") && atoi(getenv("LG_TC_NO_MULTICAST")) != 0);
-  const bool mc = use_mc && p.w_select == 0;  // per-tile W selection (final_proj heads, assignment sweeps) cannot share W
+  static const bool use_cg2 = !(getenv("LG_TC_NO_CG2") && atoi(getenv("LG_TC_NO_CG2")) != 0);
+  const bool cg2 = use_cg2 && p.w_select == 0;  // per-tile W selection (final_proj heads, assignment sweeps) cannot share W
   switch (p.epi) {
-    case TEPI_QKV: return mc ? launch_linear_t<1, TEPI_QKV, true>(p, n_tiles, stream) : launch_linear_t<1, TEPI_QKV, false>(p, n_tiles, stream);
-    case TEPI_BF16: return mc ? launch_linear_t<1, TEPI_BF16, true>(p, n_tiles, stream) : launch_linear_t<1, TEPI_BF16, false>(p, n_tiles, stream);
-    case TEPI_LN_GELU: return mc ? launch_linear_t<2, TEPI_LN_GELU, true>(p, 1, stream) : launch_linear_t<2, TEPI_LN_GELU, false>(p, 1, stream);
-    case TEPI_RESID: return mc ? launch_linear_t<1, TEPI_RESID, true>(p, n_tiles, stream) : launch_linear_t<1, TEPI_RESID, false>(p, n_tiles, stream);
-    case TEPI_F32: return mc ? launch_linear_t<1, TEPI_F32, true>(p, n_tiles, stream) : launch_linear_t<1, TEPI_F32, false>(p, n_tiles, stream);
-    case TEPI_LSE: return launch_linear_t<1, TEPI_LSE, false>(p, n_tiles, stream);
-    case TEPI_ARGMAX: return launch_linear_t<1, TEPI_ARGMAX, false>(p, n_tiles, stream);
+    case TEPI_QKV: return launch_linear_e<1, TEPI_QKV>(p, n_tiles, cg2, stream);
+    case TEPI_BF16: return launch_linear_e<1, TEPI_BF16>(p, n_tiles, cg2, stream);
+    case TEPI_LN_GELU: return launch_linear_e<2, TEPI_LN_GELU>(p, 1, cg2, stream);
+    case TEPI_RESID: return launch_linear_e<1, TEPI_RESID>(p, n_tiles, cg2, stream);
+    case TEPI_F32: return launch_linear_e<1, TEPI_F32>(p, n_tiles, cg2, stream);
+    case TEPI_LSE: return launch_linear_t<1, TEPI_LSE, false, false>(p, n_tiles, stream);
+    case TEPI_ARGMAX: return launch_linear_t<1, TEPI_ARGMAX, false, false>(p, n_tiles, stream);
   }
   return lg_set_error("launch_linear: bad epilogue");
 }
@@ -1048,6 +1117,7 @@ int tc_block(LgHandle* h, const TcBuffers& b, const SeqState& st, int layer, int
   const float* bw = h->wpk + base;
   {  // QKV (+RoPE) / [to_qk | to_v] projection
     Timer t(h, LG_K_LINEAR, stream);
+    Timer t2(h, LG_K_QKV, stream);
     TcLinParams p{};
     p.epi = TEPI_QKV; p.rope = blk == 0; p.scale = 1.f; p.bias = bw + o.bp;
     p.q = b.q; p.k = b.k; p.vt = b.vt; p.cs = cs;
@@ -1061,18 +1131,22 @@ int tc_block(LgHandle* h, const TcBuffers& b, const SeqState& st, int layer, int
     if (r) return r;
   }
   Timer t(h, LG_K_LINEAR, stream);
-  {  // out_proj / to_out -> msg
+  static const bool no_fold = getenv("LG_TC_NO_FOLD") && atoi(getenv("LG_TC_NO_FOLD")) != 0;  // debug: separate out_proj launch
+  if (no_fold) {  // out_proj / to_out -> msg
     TcLinParams p{};
     p.epi = TEPI_BF16; p.scale = 1.f; p.bias = bw + o.bo; p.out_h = b.msgh; p.out_l = b.msgl; p.ldb = LG_DIM;
     LinDesc ld{b.ctxh, b.ctxl, LG_DIM, nullptr, nullptr, 0, base + o.wo, LG_DIM, 1, 0};
     int r = run_linear(h, st, ld, p, stream);
     if (r) return r;
   }
-  {  // ffn.0 on cat([x, msg]) + LayerNorm + GELU -> h
+  {  // ffn.0 on cat([x, msg]) + LayerNorm + GELU -> h; the output projection is folded into the weights (W1f, b1f:
+     // lg_handle.h), so the GEMM reads cat([x, ctx]) and `msg` is never formed
     TcLinParams p{};
-    p.epi = TEPI_LN_GELU; p.scale = 1.f; p.bias = bw + o.b1; p.ln_g = bw + o.g; p.ln_b = bw + o.be;
+    p.epi = TEPI_LN_GELU; p.scale = 1.f; p.bias = bw + (no_fold ? o.b1 : o.b1f); p.ln_g = bw + o.g; p.ln_b = bw + o.be;
     p.out_h = b.hh; p.out_l = b.hl; p.ldb = LG_FFN;
-    LinDesc ld{b.xh, b.xl, LG_DIM, b.msgh, b.msgl, LG_DIM, base + o.w1, LG_FFN, 1, 0};
+    LinDesc ld{b.xh, b.xl, LG_DIM, no_fold ? b.msgh : b.ctxh, no_fold ? b.msgl : b.ctxl, LG_DIM, base + (no_fold ? o.w1 : o.w1f),
+               LG_FFN, 1, 0};
+    Timer t2(h, LG_K_FFN0, stream);
     int r = run_linear(h, st, ld, p, stream);
     if (r) return r;
   }
@@ -1081,6 +1155,7 @@ int tc_block(LgHandle* h, const TcBuffers& b, const SeqState& st, int layer, int
     p.epi = TEPI_RESID; p.scale = 1.f; p.bias = bw + o.b2; p.out_f32 = x; p.ldo = LG_DIM;
     p.out_h = b.xh; p.out_l = b.xl; p.ldb = LG_DIM;
     LinDesc ld{b.hh, b.hl, LG_FFN, nullptr, nullptr, 0, base + o.w2, LG_DIM, 1, 0};
+    Timer t2(h, LG_K_FFN3, stream);
     int r = run_linear(h, st, ld, p, stream);
     if (r) return r;
   }

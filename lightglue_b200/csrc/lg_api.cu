@@ -105,6 +105,24 @@ __global__ void permute_qkv_kernel(const float* __restrict__ w, const float* __r
   if (threadIdx.x == 0) bo[prow] = b[src];
 }
 
+// W1f = [W1[:, :256] | W1[:, 256:] Wo], b1f = b1 + W1[:, 256:] bo, accumulated in double (see lg_handle.h)
+__global__ void fold_out_proj_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ wo,
+                                     const float* __restrict__ bo, float* __restrict__ w1f, float* __restrict__ b1f) {
+  const int n = blockIdx.x;  // ffn.0 output channel
+  const float* row = w1 + (size_t)n * LG_FFN;
+  for (int c = threadIdx.x; c < LG_DIM; c += blockDim.x) {
+    w1f[(size_t)n * LG_FFN + c] = row[c];
+    double acc = 0.0;
+    for (int j = 0; j < LG_DIM; ++j) acc += (double)row[LG_DIM + j] * (double)wo[(size_t)j * LG_DIM + c];
+    w1f[(size_t)n * LG_FFN + LG_DIM + c] = (float)acc;
+  }
+  if (threadIdx.x == 0) {
+    double acc = (double)b1[n];
+    for (int j = 0; j < LG_DIM; ++j) acc += (double)row[LG_DIM + j] * (double)bo[j];
+    b1f[n] = (float)acc;
+  }
+}
+
 extern "C" int lg_create(const LgConfig* cfg, const float* blob, size_t n_floats, void* stream_, LgHandle** out) {
   if (!cfg || !blob || !out) return lg_set_error("lg_create: null argument");
   if (cfg->abi_version != LG_ABI_VERSION) return lg_set_error("lg_create: ABI version mismatch");
@@ -183,6 +201,12 @@ extern "C" int lg_create(const LgConfig* cfg, const float* blob, size_t n_floats
     CU(cp(bo + h->bcross.be, p, F)); p += F;
     CU(cp(bo + h->bcross.w2, p, D * F)); p += D * F;
     CU(cp(bo + h->bcross.b2, p, D)); p += D;
+    for (int blk = 0; blk < 2; ++blk) {
+      const BlockOff& o = blk == 0 ? h->bself : h->bcross;
+      float* bw = base + (blk == 0 ? 0 : h->bself.total);
+      fold_out_proj_kernel<<<(unsigned)F, 256, 0, stream>>>(bw + o.w1, bw + o.b1, bw + o.wo, bw + o.bo, bw + o.w1f, bw + o.b1f);
+      CU(cudaGetLastError());
+    }
   }
   for (int l = 0; l < L; ++l) {  // packed: final_proj.w [256,256] | final_proj.b [256] | matchability.w [256] | .b [1] (+pad)
     const size_t dst = h->o_assign + (size_t)l * ASSIGN_BLOB_PAD;
@@ -427,8 +451,10 @@ extern "C" int lg_forward(LgHandle* h, const LgInputs* in, const LgOutputs* out,
   h->launches = 0;
   const bool early = h->cfg.depth_confidence > 0, prune = h->cfg.width_confidence > 0;
   if (out->log_assignment && (early || prune)) return lg_set_error("lg_forward: log_assignment needs adaptivity off");
-  RC(check_outputs(out));
   if (M == 0 || N == 0) {  // lightglue.py:568-588: no keypoints -> nothing matched, stop = 1
+    // (a zero-sized side may come with null pointers; the non-empty side's outputs must exist)
+    if ((M > 0 && (!out->matches0 || !out->matching_scores0)) || (N > 0 && (!out->matches1 || !out->matching_scores1)))
+      return lg_set_error("LgOutputs: required output pointer is null");
     const long n0 = (long)B * M, n1 = (long)B * N;
     long mx = n0 > n1 ? n0 : n1;
     if (mx < B) mx = B;
@@ -439,6 +465,7 @@ extern "C" int lg_forward(LgHandle* h, const LgInputs* in, const LgOutputs* out,
     h->launches = 1;
     return 0;
   }
+  RC(check_outputs(out));
   if (!in->kpts0 || !in->kpts1 || !in->desc0 || !in->desc1) return lg_set_error("lg_forward: null input tensor");
   Workspace w;
   carve(h, B, M, N, (char*)workspace, &w);

@@ -7,9 +7,12 @@
 #include "lg_tc.h"
 
 // packed per-block fp32 layout (floats):
-//   Wp [Np,256] | bp [Np] | Wo [256,256] | bo | W1 [512,512] | b1 | ln.g | ln.b | W2 [256,512] | b2
+//   Wp [Np,256] | bp [Np] | Wo [256,256] | bo | W1 [512,512] | b1 | ln.g | ln.b | W2 [256,512] | b2 | W1f [512,512] | b1f
+// W1f / b1f: ffn.0 with the attention output projection folded in (tensor-core path):
+//   ffn.0(cat[x, out_proj(ctx)]) = W1[:, :256] x + (W1[:, 256:] Wo) ctx + (b1 + W1[:, 256:] bo)
+// so the block runs cat[x, ctx] through ONE GEMM and `msg` never exists (lightglue.py:171-172, 227-229).
 struct BlockOff {
-  size_t wp, bp, wo, bo, w1, b1, g, be, w2, b2, total;
+  size_t wp, bp, wo, bo, w1, b1, g, be, w2, b2, w1f, b1f, total;
 };
 inline BlockOff block_off(size_t np) {
   BlockOff o;
@@ -24,6 +27,8 @@ inline BlockOff block_off(size_t np) {
   o.be = c; c += LG_FFN;
   o.w2 = c; c += (size_t)LG_DIM * LG_FFN;
   o.b2 = c; c += LG_DIM;
+  o.w1f = c; c += (size_t)LG_FFN * LG_FFN;
+  o.b1f = c; c += LG_FFN;
   o.total = c;
   return o;
 }

@@ -36,19 +36,60 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug must never hang the GPU box.  After ~2^20 failed probes the waiter records
-// a site code in g_tc_timeout (read back by lg_debug_timeout_code()) and gives up; the kernel then
-// finishes with garbage instead of dead-locking, and the host can report where it stalled.
-// dbg points at 32 words; word `site` keeps the first code recorded there: 0x80000000 | extra << 12 | thread.
+// Bounded spin: a protocol bug must never hang the GPU box.  After ~2^18 failed probes the waiter records
+// a site code (read back by lg_debug_timeout_code()) and gives up; the kernel then finishes with garbage instead
+// of dead-locking, and the host can report where it stalled.
+// dbg points at 32 words; word `site` keeps the first code recorded there: 0x80000000 | extra << 12 | thread;
+// word 31 is the "some wait has timed out" flag: once it is set every other long wait gives up after 64 probes,
+// so a broken pipeline drains in milliseconds instead of minutes.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, uint32_t site,
                                           uint32_t extra = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 18)) {
-      if (dbg) atomicCAS(dbg + (site & 31), 0u, 0x80000000u | ((extra & 0xffff) << 12) | (threadIdx.x & 0xfff));
+    ++spins;
+    if (spins == 64 && dbg && *reinterpret_cast<volatile unsigned int*>(dbg + 31) != 0u) return;
+    if (spins > (1u << 18)) {
+      if (dbg) {
+        atomicCAS(dbg + (site & 31), 0u, 0x80000000u | ((extra & 0xffff) << 12) | (threadIdx.x & 0xfff));
+        atomicExch(dbg + 31, 1u);
+      }
       return;
     }
   }
+}
+// same, acquiring at cluster scope (the arrival may come from the peer CTA of a pair)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, unsigned int* dbg, uint32_t site,
+                                                  uint32_t extra = 0) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    ++spins;
+    if (spins == 64 && dbg && *reinterpret_cast<volatile unsigned int*>(dbg + 31) != 0u) return;
+    if (spins > (1u << 18)) {
+      if (dbg) {
+        atomicCAS(dbg + (site & 31), 0u, 0x80000000u | ((extra & 0xffff) << 12) | (threadIdx.x & 0xfff));
+        atomicExch(dbg + 31, 1u);
+      }
+      return;
+    }
+  }
+}
+// CTA pairs (cta_group::2): in the shared::cluster window bit 24 of a shared-memory address selects the CTA of the
+// pair; clearing it addresses the same offset in the even ("leader") CTA
+constexpr uint32_t PAIR_LEADER_MASK = 0xFEFFFFFFu;
+// arrive on the barrier at this offset in the LEADER CTA of the pair (from either CTA), release at cluster scope
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PAIR_LEADER_MASK) : "memory");
 }
 
 // ---------------------------------------------------------------- TMA
@@ -70,14 +111,20 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
-// multicast load: the box lands at the same shared-memory offset in every CTA of `mask` and completes tx bytes on the
-// barrier at the same offset in each of them
-__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar,
-                                               uint16_t mask) {
+// CTA-pair loads (cta_group::2): the box lands in THIS CTA's shared memory, the transaction bytes complete on the
+// barrier at `bar`'s offset in the LEADER CTA (the single MMA-issuing thread of the pair waits there)
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* m, int c0, int c1, uint64_t* bar) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], "
-      "[%2], %6;" ::"r"(smem_u32(smem_dst)),
-      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(m), "r"(smem_u32(bar) & PAIR_LEADER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_cg2(void* smem_dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(m), "r"(smem_u32(bar) & PAIR_LEADER_MASK), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -118,6 +165,17 @@ template <int NCOLS>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // same warp that allocated
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
 }
+// CTA-pair variants: the same warp of BOTH CTAs of the pair executes them with the same shared-memory offset
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -144,9 +202,19 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// same, arriving on the barrier at this offset in every CTA of `mask` (stages shared through multicast loads)
-__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+// CTA pair: D[tmem of both CTAs] (+)= A[256 rows: 128 in each CTA's smem] * B[N rows: N/2 in each CTA's smem];
+// issued by one thread of the LEADER CTA, descriptors are shared-memory offsets valid in both CTAs
+__device__ __forceinline__ void mma_ss_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the pair's MMAs issued so far have completed) on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void mma_commit_cg2(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                    smem_u32(bar)),
                "h"(mask)
                : "memory");

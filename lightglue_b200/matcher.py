@@ -505,7 +505,8 @@ class LightGlue(nn.Module):
             return {}
         lib = _cabi.load()
         res = {}
-        for name, kc in (("attention", 0), ("linear", 1), ("assign", 2), ("other", 3), ("assign_matrix", 4)):
+        for name, kc in (("attention", 0), ("linear", 1), ("assign", 2), ("other", 3), ("assign_matrix", 4), ("qkv", 5),
+                         ("ffn0", 6), ("ffn3", 7), ("assign_stage", 8)):
             ms, cnt = C.c_double(), C.c_int64()
             _cabi.check(lib.lg_kernel_time_ms(self._handle[0], kc, C.byref(ms), C.byref(cnt)), "lg_kernel_time_ms")
             res[name] = (ms.value, cnt.value)
