@@ -4,20 +4,14 @@
 // sequence in blocks of 64:
 //   S_t = Q_t K_j^T      tcgen05.mma  M=128 N=64 K=64    operands in shared memory (TMA, 128B swizzle)
 //   P_t = exp2(c S_t - c m_t)   softmax warpgroup t: TMEM -> registers -> fp16 -> TMEM (in place over S_t)
-//   O_t += P_t [V_j | 1] tcgen05.mma  M=128 N=80 K=64    A = P_t from TMEM, B = V^T tile in shared memory
-//                        extended by a constant row of ones: column 64 of O_t is the softmax denominator,
-//                        accumulated by the tensor core from the same fp16 P the numerator uses.
-// S is double-buffered per query tile: S_t(j+1) is computed while warpgroup t is still busy with the
-// softmax of S_t(j), so the softmax warps (the MUFU pipe is the bound at head_dim 64) never wait for
-// the tensor core.  O(N) softmax: running max with lazy rescaling (O is only rescaled when the row
-// max grows by more than 2^8), one division at the end.
-// FAST (LG_PREC_BF16): exponentials go through ex2.approx.f16x2 on (s - m) * c computed in fp32 -- the
-// result is directly the packed fp16 P operand.
-// TMEM map (512 columns): S[t][b] at 128*t + 64*b (P aliases its first 32 columns) | O0 256-335 | O1 384-463.
-// Warp roles (384 threads = 3 warpgroups): warpgroup 0 = {warp 0 TMA producer, warp 1 TMEM owner + MMA
-// issuer of tile 0, warp 2 MMA issuer of tile 1, 1 idle warp} shrinks its registers (setmaxnreg.dec);
-// warpgroups 1 and 2 are the softmax
-// warpgroups of query tile 0 / 1 (one query row per thread; warp w reads TMEM lanes 32*(w%4)..).
+//   O_t += P_t V_j       tcgen05.mma  M=128 N=64 K=64    A = P_t from TMEM, B = V^T tile in shared memory
+// O(N) softmax: running max with lazy rescaling (O is only rescaled when the row max grows by more than 2^8),
+// the denominator is summed in registers (packed f32x2 adds), one division at the end.
+// 256 TMEM columns and ~100 KB of shared memory per CTA, so TWO CTAs are resident per SM: four softmax warps per
+// scheduler hide the TMEM-load / barrier latencies of a block.  TMEM map: S0 0-63 | S1 64-127 | O0 128-191 | O1 192-255.
+// Warp roles (384 threads = 3 warpgroups): warpgroup 0 = {warp 0 TMA producer, warp 1 TMEM owner + MMA issuer of
+// tile 0, warp 2 MMA issuer of tile 1, 1 idle warp} shrinks its registers (setmaxnreg.dec); warpgroups 1 and 2 are
+// the softmax warpgroups of query tile 0 / 1 (one query row per thread; warp w reads TMEM lanes 32*(w%4)..).
 #include <stdlib.h>
 
 #include "lg_handle.h"
@@ -29,14 +23,8 @@ namespace {
 
 constexpr int QT = 128;          // query rows per tile
 constexpr int KB = 64;           // keys per block
-constexpr int KV_STAGES = 8;
 constexpr int Q_TILE_BYTES = QT * 64 * 2;   // 16 KB
 constexpr int K_TILE_BYTES = KB * 64 * 2;   // 8 KB
-constexpr int V_ROWS = 80;                  // 64 value channels + the ones row + 15 zero rows (N % 16 == 0)
-constexpr int V_TILE_BYTES = V_ROWS * 128;  // 10 KB: [80 rows][64 keys]
-constexpr int KV_STAGE_BYTES = K_TILE_BYTES + V_TILE_BYTES;  // 18 KB
-constexpr int V_TMA_BYTES = 64 * 128;       // bytes TMA writes into the V tile
-constexpr uint32_t TM_S = 0, TM_O = 256;
 constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;  // dh^-0.5 * log2(e)
 
 struct AttnParams {
@@ -55,11 +43,47 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ uint32_t ex2_f16x2(float x0, float x1) {  // {2^x0, 2^x1} as packed fp16 (x0 in the low half)
-  uint32_t h, y;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(h));
-  return y;
+// packed fp32 pairs (sm_100 FFMA2 / FADD2: one issue slot for two elements)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// pipeline waits of this kernel: try_wait with a suspend-time hint, so that a waiting warp sleeps in hardware instead
+// of spending issue slots on polling (the softmax warps need them); bounded like tc::mbar_wait
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned int* dbg, uint32_t site, uint32_t extra = 0) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) return;
+    ++spins;
+    if (spins == 8 && dbg && *reinterpret_cast<volatile unsigned int*>(dbg + 31) != 0u) return;
+    if (spins > (1u << 14)) {
+      if (dbg) {
+        atomicCAS(dbg + (site & 31), 0u, 0x80000000u | ((extra & 0xffff) << 12) | (threadIdx.x & 0xfff));
+        atomicExch(dbg + 31, 1u);
+      }
+      return;
+    }
+  }
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
@@ -75,268 +99,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(384, 1) tc_attention_kernel(const __grid_constant__ AttnParams p) {
-  const int s = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * 2 * QT;
-  const int len_q = p.st.len[s];
-  if (r0 >= len_q || lg_pair_stopped(p.st, s)) return;
-  const int skv = (s + p.kv_shift) % p.st.S;
-  const int len_kv = p.st.len[skv];
-  const int nkv = (len_kv + KB - 1) / KB;
-  const int nt = (len_q - r0 > QT) ? 2 : 1;  // live query tiles in this CTA
-
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // align by OFFSETTING the shared array (not by rebuilding a pointer from an integer): the compiler keeps the
-  // shared address space and emits LDS / STS instead of generic LD / ST for everything derived from it
-  uint8_t* smem = smem_raw + ((1024u - (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(smem_raw)) & 1023u)) & 1023u);
-  uint8_t* sq = smem;                                  // 2 x 16 KB
-  uint8_t* skvb = smem + 2 * Q_TILE_BYTES;             // KV_STAGES x 18 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(skvb + KV_STAGES * KV_STAGE_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = kv_full + KV_STAGES;
-  uint64_t* s_full = kv_empty + KV_STAGES;   // [t][b] -> s_full[2 * t + b]
-  uint64_t* p_full = s_full + 4;             // [t][b]: the softmax may run one block ahead of the MMA warp,
-                                             // so P(j) and P(j+1) need separate barriers (no phase lapping)
-  uint64_t* o_done = p_full + 4;             // [2] one phase per block (only ever tested for block j-1 during block j)
-  uint64_t* o_final = o_done + 2;            // [2] single phase: last P V of the tile retired.  (The softmax
-                                             // runs ahead of the MMA warp, so a parity test on o_done for the
-                                             // last block could alias an older phase.)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
-
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-
-  // constant rows 64..79 of every V^T tile: row 64 = ones (fp16), rows 65..79 = zeros
-  for (int e = threadIdx.x; e < KV_STAGES * 128; e += blockDim.x) {
-    const int tile = e / 128, w = e % 128;  // 128 x 16-byte words per constant region
-    uint8_t* base = skvb + tile * KV_STAGE_BYTES + K_TILE_BYTES + V_TMA_BYTES;
-    const uint32_t v = (w < 8) ? 0x3C003C00u : 0u;
-    reinterpret_cast<uint4*>(base)[w] = make_uint4(v, v, v, v);
-  }
-  fence_proxy_async();
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.q_map);
-    tma_prefetch_desc(&p.k_map);
-    tma_prefetch_desc(&p.vt_map);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], nt); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); }
-    for (int t = 0; t < 2; ++t) { mbar_init(&o_done[t], 1); mbar_init(&o_final[t], 1); }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    if (nkv > 0) {
-      if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (elect_one()) {
-          mbar_arrive_expect_tx(q_full, 2 * Q_TILE_BYTES);
-          tma_load_3d(sq, &p.q_map, 0, r0, s * LG_HEADS + h, q_full);
-          tma_load_3d(sq + Q_TILE_BYTES, &p.q_map, 0, r0 + QT, s * LG_HEADS + h, q_full);
-          for (int j = 0; j < nkv; ++j) {
-            const int stage = j % KV_STAGES, round = j / KV_STAGES;
-            mbar_wait(&kv_empty[stage], (round & 1) ^ 1, p.dbg, 1, j);
-            uint8_t* dst = skvb + stage * KV_STAGE_BYTES;
-            mbar_arrive_expect_tx(&kv_full[stage], K_TILE_BYTES + V_TMA_BYTES);
-            tma_load_3d(dst, &p.k_map, 0, j * KB, skv * LG_HEADS + h, &kv_full[stage]);
-            tma_load_3d(dst + K_TILE_BYTES, &p.vt_map, j * KB, 0, skv * LG_HEADS + h, &kv_full[stage]);
-          }
-        }
-      } else if (warp - 1 < nt) {
-        // ------------------------------------------------------------------ MMA issuers: warp 1 -> tile 0, warp 2 -> tile 1
-        // (one issuing warp per query tile: the single-thread issue path -- descriptor moves to uniform
-        //  registers, tcgen05.mma, tcgen05.commit -- is long enough to bound the kernel if one warp serves both)
-        const int t = warp - 1;
-        constexpr uint32_t idesc_qk = make_idesc(QT, KB, false);      // M=128 N=64, fp16
-        constexpr uint32_t idesc_pv = make_idesc(QT, V_ROWS, false);  // M=128 N=80, fp16
-        const uint64_t qdesc = make_sdesc_sw128(smem_u32(sq + t * Q_TILE_BYTES));
-        const uint64_t kdesc0 = make_sdesc_sw128(smem_u32(skvb));
-        const uint64_t vdesc0 = make_sdesc_sw128(smem_u32(skvb + K_TILE_BYTES));
-        const uint32_t ts_addr = tmem_base + TM_S + t * 128;
-        const uint32_t to_addr = tmem_base + TM_O + t * 128;
-        auto issue_qk = [&](int j) {  // S[t][j & 1] = Q_t K_j^T   (called by one elected lane)
-          const uint64_t kdesc = kdesc0 + (uint64_t)((j % KV_STAGES) * (KV_STAGE_BYTES >> 4));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma_ss(ts_addr + (j & 1) * 64, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
-          mma_commit(&s_full[2 * t + (j & 1)]);
-        };
-        mbar_wait(q_full, 0, p.dbg, 2);
-        for (int j = 0; j < 2 && j < nkv; ++j) {  // prologue: S_t(0), S_t(1)
-          mbar_wait(&kv_full[j % KV_STAGES], 0, p.dbg, 3);
-          tc_fence_after();
-          if (elect_one()) issue_qk(j);
-          __syncwarp();
-        }
-        for (int j = 0; j < nkv; ++j) {
-          const int stage = j % KV_STAGES;
-          if (j + 2 < nkv) mbar_wait(&kv_full[(j + 2) % KV_STAGES], ((j + 2) / KV_STAGES) & 1, p.dbg, 4, j);
-          mbar_wait(&p_full[2 * t + (j & 1)], (j >> 1) & 1, p.dbg, 5, j * 2 + t);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t vdesc = vdesc0 + (uint64_t)(stage * (KV_STAGE_BYTES >> 4));
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)  // 4 x 16 keys; P_t(j) lives in the first 32 columns of S[t][j & 1]
-              mma_ts(to_addr, ts_addr + (j & 1) * 64 + ks * 8, vdesc + 2 * ks, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
-            mma_commit(&kv_empty[stage]);  // this tile is done with K_j / V_j (the barrier expects nt arrivals)
-            mma_commit(&o_done[t]);        // P_t(j) V_j retired (phase j): gates the lazy rescaling of O_t
-            // the tensor pipe executes one thread's MMAs in issue order: S_t(j+2) cannot overwrite P_t(j)
-            // before P_t(j) V_j has read it
-            if (j + 2 < nkv) issue_qk(j + 2);
-            else if (j + 1 == nkv) mma_commit(&o_final[t]);  // single phase: everything for tile t has retired
-          }
-          __syncwarp();
-        }
-      }
-    }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-    // ------------------------------------------------------------------ softmax warpgroups
-    const int t = (warp - 4) / 4;
-    const int quarter = warp % 4;
-    const int row = quarter * 32 + lane;
-    const int r = r0 + t * QT + row;
-    const long off = ((long)s * p.st.Lp + r) * LG_DIM + h * LG_HDIM;
-    if (nkv > 0) {
-      if (t < nt) {
-        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-        const uint32_t ts0 = tmem_base + lane_off + TM_S + t * 128;
-        const uint32_t to = tmem_base + lane_off + TM_O + t * 128;
-        float m_used = -INFINITY;
-        uint32_t sv[2][32];  // the whole 64-column S row of this thread: TMEM is read once per block
-        for (int j = 0; j < nkv; ++j) {
-          const uint32_t ts = ts0 + (j & 1) * 64;
-          mbar_wait(&s_full[2 * t + (j & 1)], (j >> 1) & 1, p.dbg, 6, j * 2 + t);
-          tc_fence_after();
-          const int valid = len_kv - j * KB;  // columns >= valid are padding (last block only)
-          tmem_ld32(ts, sv[0]);
-          tmem_ld32(ts + 32, sv[1]);
-          tmem_ld_wait();
-          if (valid < KB) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;  // -inf
-          }
-          float mx0 = -INFINITY, mx1 = -INFINITY;  // two chains for ILP
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              mx0 = max3(mx0, __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
-              mx1 = max3(mx1, __uint_as_float(sv[c][i + 2]), __uint_as_float(sv[c][i + 3]));
-            }
-          const float mx = fmaxf(mx0, mx1);
-          // lazy rescale: keep the old reference max unless the new one exceeds it by > 2^8
-          float alpha = 1.f;
-          bool need = false;
-          if (mx > m_used) {
-            if (m_used == -INFINITY) { m_used = mx; }
-            else if ((mx - m_used) * SCALE_LOG2 > 8.f) { alpha = ex2((m_used - mx) * SCALE_LOG2); m_used = mx; need = true; }
-          }
-          if (__any_sync(0xffffffffu, need)) {
-            // O_t may still be receiving P_t(j-1) V_{j-1} (S_t(j) was issued before it): wait for its commit
-            mbar_wait(&o_done[t], (j - 1) & 1, p.dbg, 7, j * 2 + t);
-            tc_fence_after();
-            uint32_t o32[32];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              tmem_ld32(to + c * 32, o32);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o32[i] = __float_as_uint(__uint_as_float(o32[i]) * alpha);
-              tmem_st32(to + c * 32, o32);
-            }
-            uint32_t o16[16];
-            tmem_ld16(to + 64, o16);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o16[i] = __float_as_uint(__uint_as_float(o16[i]) * alpha);
-            tmem_st16(to + 64, o16);
-          }
-          // P = exp2(c s - c m) as fp16, written over the first 32 columns of S[t][j & 1]
-          const float mc = m_used * SCALE_LOG2;
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float x0 = fmaf(__uint_as_float(sv[c][2 * i]), SCALE_LOG2, -mc);
-              const float x1 = fmaf(__uint_as_float(sv[c][2 * i + 1]), SCALE_LOG2, -mc);
-              if (FAST) {
-                pk[i] = ex2_f16x2(x0, x1);
-              } else {
-                const __half2 hh = __floats2half2_rn(ex2(x0), ex2(x1));
-                pk[i] = *reinterpret_cast<const uint32_t*>(&hh);
-              }
-            }
-            tmem_st16(ts + c * 16, pk);
-          }
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&p_full[2 * t + (j & 1)]);
-        }
-        // ---- epilogue: O[:, 0:64] / O[:, 64] -> ctx (heads concatenated h-major, lightglue.py:171)
-        mbar_wait(&o_final[t], 0, p.dbg, 8, t);
-        tc_fence_after();
-        uint32_t o16[16];
-        tmem_ld16(to + 64, o16);
-        tmem_ld_wait();
-        const float l = __uint_as_float(o16[0]);
-        const float inv = l > 0.f ? 1.f / l : 0.f;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          tmem_ld32(to + c * 32, sv[c]);
-          tmem_ld_wait();
-          if (r < len_q) {
-            uint32_t ph[16], pl[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float a = __uint_as_float(sv[c][2 * i]) * inv, b = __uint_as_float(sv[c][2 * i + 1]) * inv;
-              ph[i] = pack_bf16x2(a, b);
-              pl[i] = pack_bf16x2_lo(a, b, ph[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              reinterpret_cast<uint4*>(p.ctxh + off + c * 32)[i] = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
-              if (p.ctxl)
-                reinterpret_cast<uint4*>(p.ctxl + off + c * 32)[i] = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
-            }
-          }
-        }
-      }
-    } else if (r < len_q) {
-      // no keys: zeros (lightglue.py:114-115)
-      for (int i = 0; i < 8; ++i) {
-        reinterpret_cast<uint4*>(p.ctxh + off)[i] = make_uint4(0, 0, 0, 0);
-        if (p.ctxl) reinterpret_cast<uint4*>(p.ctxl + off)[i] = make_uint4(0, 0, 0, 0);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Variant B: same tiling (256 query rows per CTA, 64-key blocks) but only 256 TMEM columns and ~100 KB of
-// shared memory per CTA, so TWO CTAs are resident per SM: four softmax warps per scheduler instead of two
-// hide the TMEM-load / barrier latencies of a block.  S is single-buffered (S_t 64 columns, P in place),
-// O_t has 64 columns and the softmax denominator is summed in registers.
-// TMEM map (256 columns): S0 0-63 | S1 64-127 | O0 128-191 | O1 192-255.
-// ------------------------------------------------------------------------------------------------
 constexpr int B_KV_STAGES = 4;
 constexpr int B_V_TILE_BYTES = 64 * 128;                      // [64 d rows][64 keys]
 constexpr int B_STAGE_BYTES = K_TILE_BYTES + B_V_TILE_BYTES;  // 16 KB
 
-template <bool FAST>
 __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_constant__ AttnParams p) {
   pdl_launch_dependents();
   pdl_wait();  // the sequence lengths read right below belong to the dependency chain
@@ -389,7 +155,7 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
           tma_load_3d(sq + Q_TILE_BYTES, &p.q_map, 0, r0 + QT, s * LG_HEADS + h, q_full);
           for (int j = 0; j < nkv; ++j) {
             const int stage = j % B_KV_STAGES, round = j / B_KV_STAGES;
-            mbar_wait(&kv_empty[stage], (round & 1) ^ 1, p.dbg, 1, j);
+            mbar_wait_sleep(&kv_empty[stage], (round & 1) ^ 1, p.dbg, 1, j);
             uint8_t* dst = skvb + stage * B_STAGE_BYTES;
             mbar_arrive_expect_tx(&kv_full[stage], B_STAGE_BYTES);
             tma_load_3d(dst, &p.k_map, 0, j * KB, skv * LG_HEADS + h, &kv_full[stage]);
@@ -412,15 +178,15 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
           for (int k = 0; k < 4; ++k) mma_ss(ts_addr, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
           mma_commit(&s_full[t]);
         };
-        mbar_wait(q_full, 0, p.dbg, 2);
-        mbar_wait(&kv_full[0], 0, p.dbg, 3);
+        mbar_wait_sleep(q_full, 0, p.dbg, 2);
+        mbar_wait_sleep(&kv_full[0], 0, p.dbg, 3);
         tc_fence_after();
         if (elect_one()) issue_qk(0);
         __syncwarp();
         for (int j = 0; j < nkv; ++j) {
           const int stage = j % B_KV_STAGES;
-          if (j + 1 < nkv) mbar_wait(&kv_full[(j + 1) % B_KV_STAGES], ((j + 1) / B_KV_STAGES) & 1, p.dbg, 4, j);
-          mbar_wait(&p_full[t], j & 1, p.dbg, 5, j * 2 + t);
+          if (j + 1 < nkv) mbar_wait_sleep(&kv_full[(j + 1) % B_KV_STAGES], ((j + 1) / B_KV_STAGES) & 1, p.dbg, 4, j);
+          mbar_wait_sleep(&p_full[t], j & 1, p.dbg, 5, j * 2 + t);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t vdesc = vdesc0 + (uint64_t)(stage * (B_STAGE_BYTES >> 4));
@@ -451,7 +217,7 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
         float m_used = -INFINITY, l = 0.f;
         uint32_t sv[2][32];
         for (int j = 0; j < nkv; ++j) {
-          mbar_wait(&s_full[t], j & 1, p.dbg, 6, j * 2 + t);
+          mbar_wait_sleep(&s_full[t], j & 1, p.dbg, 6, j * 2 + t);
           tc_fence_after();
           const int valid = len_kv - j * KB;
           tmem_ld32(ts, sv[0]);
@@ -491,28 +257,36 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
             }
             l *= alpha;
           }
-          const float mc = m_used * SCALE_LOG2;
-          float l0 = 0.f, l1 = 0.f;
+          // P = exp2(c s - c m): the scale-and-shift and the row sum run as packed f32x2 operations
+          const uint64_t sc2 = pack2(SCALE_LOG2, SCALE_LOG2);
+          const float nmc = -m_used * SCALE_LOG2;
+          const uint64_t nm2 = pack2(nmc, nmc);
+          uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float x0 = fmaf(__uint_as_float(sv[c][2 * i]), SCALE_LOG2, -mc);
-              const float x1 = fmaf(__uint_as_float(sv[c][2 * i + 1]), SCALE_LOG2, -mc);
+              float x0, x1;
+              unpack2(fma2(pack2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2), x0, x1);
               const float e0 = ex2(x0), e1 = ex2(x1);
-              l0 += e0; l1 += e1;
+              if (i & 1) lb = add2(lb, pack2(e0, e1));
+              else la = add2(la, pack2(e0, e1));
               const __half2 hh = __floats2half2_rn(e0, e1);
               pk[i] = *reinterpret_cast<const uint32_t*>(&hh);
             }
             tmem_st16(ts + c * 16, pk);
           }
-          l += l0 + l1;
+          {
+            float a0, a1;
+            unpack2(add2(la, lb), a0, a1);
+            l += a0 + a1;
+          }
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&p_full[t]);
         }
-        mbar_wait(&o_final[t], 0, p.dbg, 8, t);
+        mbar_wait_sleep(&o_final[t], 0, p.dbg, 8, t);
         tc_fence_after();
         const float inv = l > 0.f ? 1.f / l : 0.f;
 #pragma unroll
@@ -548,124 +322,6 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
   if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
-// ------------------------------------------------------------------------------------------------
-// CUDA-core reference kernel on the same fp16 operands (debug comparator: LG_TC_ATTN_REF=1)
-// ------------------------------------------------------------------------------------------------
-#define AT 64
-#define ALD 65
-__global__ void __launch_bounds__(256) attn_ref_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
-                                                       const __half* __restrict__ vt, __nv_bfloat16* __restrict__ ctxh,
-                                                       __nv_bfloat16* __restrict__ ctxl, int kv_shift, SeqState st) {
-  const int s = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * AT;
-  const int len_q = st.len[s];
-  if (r0 >= len_q || lg_pair_stopped(st, s)) return;
-  const int skv = (s + kv_shift) % st.S;
-  const int len_kv = st.len[skv];
-  extern __shared__ float sm[];
-  float* Qt = sm;
-  float* Kt = Qt + AT * ALD;
-  float* Vs = Kt + AT * ALD;  // [kv][d]
-  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
-  const __half* qb = q + (((long)s * LG_HEADS + h) * st.Lp + r0) * LG_HDIM;
-  const __half* kb = k + ((long)skv * LG_HEADS + h) * st.Lp * LG_HDIM;
-  const __half* vb = vt + ((long)skv * LG_HEADS + h) * LG_HDIM * st.Lp;
-  for (int e = tid; e < AT * 64; e += 256) {
-    const int row = e / 64, d = e % 64;
-    Qt[d * ALD + row] = __half2float(qb[(long)row * LG_HDIM + d]);
-  }
-  float o[4][4], mrow[4], lrow[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    mrow[i] = -INFINITY; lrow[i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
-  }
-  for (int c0 = 0; c0 < len_kv; c0 += AT) {
-    __syncthreads();
-    for (int e = tid; e < AT * 64; e += 256) {
-      const int row = e / 64, d = e % 64;
-      Kt[d * ALD + row] = __half2float(kb[(long)(c0 + row) * LG_HDIM + d]);
-      const int d2 = e / 64, kv = e % 64;
-      Vs[kv * 64 + d2] = __half2float(vb[(long)d2 * st.Lp + c0 + kv]);
-    }
-    __syncthreads();
-    float sc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) sc[i][j] = 0.f;
-#pragma unroll 8
-    for (int d = 0; d < 64; ++d) {
-      float af[4], bf[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) af[i] = Qt[d * ALD + ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = Kt[d * ALD + tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) sc[i][j] = fmaf(af[i], bf[j], sc[i][j]);
-    }
-    float alpha[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        sc[i][j] = (c0 + tx * 4 + j < len_kv) ? sc[i][j] * 0.125f : -INFINITY;
-        mx = fmaxf(mx, sc[i][j]);
-      }
-#pragma unroll
-      for (int off = 1; off < 16; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-      const float mnew = fmaxf(mrow[i], mx);
-      alpha[i] = expf(mrow[i] - mnew);
-      float rs = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { sc[i][j] = expf(sc[i][j] - mnew); rs += sc[i][j]; }
-#pragma unroll
-      for (int off = 1; off < 16; off <<= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
-      lrow[i] = lrow[i] * alpha[i] + rs;
-      mrow[i] = mnew;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) Kt[(tx * 4 + j) * ALD + ty * 4 + i] = sc[i][j];
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o[i][j] *= alpha[i];
-#pragma unroll 8
-    for (int kv = 0; kv < 64; ++kv) {
-      float af[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) af[i] = Kt[kv * ALD + ty * 4 + i];
-      const float4 bv = *reinterpret_cast<const float4*>(Vs + kv * 64 + tx * 4);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        o[i][0] = fmaf(af[i], bv.x, o[i][0]); o[i][1] = fmaf(af[i], bv.y, o[i][1]);
-        o[i][2] = fmaf(af[i], bv.z, o[i][2]); o[i][3] = fmaf(af[i], bv.w, o[i][3]);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = r0 + ty * 4 + i;
-    if (r >= len_q) continue;
-    const float inv = lrow[i] > 0.f ? 1.f / lrow[i] : 0.f;
-    const long off = ((long)s * st.Lp + r) * LG_DIM + h * LG_HDIM + tx * 4;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float val = o[i][j] * inv;
-      const __nv_bfloat16 hi = __float2bfloat16_rn(val);
-      ctxh[off + j] = hi;
-      if (ctxl) ctxl[off + j] = __float2bfloat16_rn(val - __bfloat162float(hi));
-    }
-  }
-}
-
 struct AttnMapCache {
   const void* q; const void* k; const void* vt; int S, Lp;
   CUtensorMap qm, km, vm;
@@ -673,17 +329,10 @@ struct AttnMapCache {
 }  // namespace
 
 int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shift, const __half* kbuf, cudaStream_t stream) {
-  static const bool use_ref = getenv("LG_TC_ATTN_REF") && atoi(getenv("LG_TC_ATTN_REF")) != 0;
   h->launches += 1;
-  if (use_ref) {
-    const size_t smem = (2 * AT * ALD + AT * 64) * sizeof(float);
-    if (int r = lg_func_smem_once((const void*)attn_ref_kernel, (int)smem)) return r;
-    attn_ref_kernel<<<dim3(st.Lp / AT, LG_HEADS, st.S), 256, smem, stream>>>(b.q, kbuf, b.vt, b.ctxh, b.ctxl, kv_shift, st);
-    LG_CHECK_LAUNCH();
-    return 0;
-  }
-  // tensor maps depend only on (buffers, S, Lp): cache the last two sets (self: k = b.k, cross: k = b.q)
-  static thread_local AttnMapCache cache[2];  // keyed by buffer pointers: device addresses are unique per device (UVA)
+  // tensor maps depend only on (buffers, S, Lp): cache the last two sets (self: k = b.k, cross: k = b.q); the
+  // buffer addresses are unique per device (UVA), so the cache is safe with several devices in one process
+  static thread_local AttnMapCache cache[2];
   AttnMapCache* c = nullptr;
   for (auto& e : cache)
     if (e.q == b.q && e.k == kbuf && e.vt == b.vt && e.S == st.S && e.Lp == st.Lp) c = &e;
@@ -699,35 +348,23 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
   AttnParams p;
   p.q_map = c->qm; p.k_map = c->km; p.vt_map = c->vm;
   p.ctxh = b.ctxh; p.ctxl = b.ctxl; p.kv_shift = kv_shift; p.st = st; p.dbg = h->tc.dbg;
-  static const int variant = getenv("LG_TC_ATTN_V") ? atoi(getenv("LG_TC_ATTN_V")) : 2;
   dim3 grid((st.Lp + 2 * QT - 1) / (2 * QT), LG_HEADS, st.S);
   p.rows_per_cta = 2 * QT;
-  if (variant == 2) {
-    if ((long)grid.x * grid.y * grid.z < 2 * lg_num_sms()) {  // fewer CTAs than resident slots: one query tile per CTA instead
-      p.rows_per_cta = QT;
-      grid.x = st.Lp / QT;
-    }
-    constexpr int smem2 = 2 * Q_TILE_BYTES + B_KV_STAGES * B_STAGE_BYTES + 1024 + 256;
-    if (int r = lg_func_smem_once((const void*)tc_attention2_kernel<true>, smem2)) return r;
-    if (int r = lg_func_smem_once((const void*)tc_attention2_kernel<false>, smem2)) return r;
-    cudaLaunchConfig_t cfg{};
-    cudaLaunchAttribute at[1];
-    cfg.gridDim = grid; cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem2; cfg.stream = stream;
-    if (tc_use_pdl()) {
-      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      at[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-    }
-    const cudaError_t e = h->cfg.precision == LG_PREC_BF16 ? cudaLaunchKernelEx(&cfg, tc_attention2_kernel<true>, p)
-                                                          : cudaLaunchKernelEx(&cfg, tc_attention2_kernel<false>, p);
-    if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
-    return 0;
+  if ((long)grid.x * grid.y * grid.z < 2 * lg_num_sms()) {  // fewer CTAs than resident slots: one query tile per CTA instead
+    p.rows_per_cta = QT;
+    grid.x = st.Lp / QT;
   }
-  constexpr int smem = 2 * Q_TILE_BYTES + KV_STAGES * KV_STAGE_BYTES + 1024 + 256;
-  if (int r = lg_func_smem_once((const void*)tc_attention_kernel<true>, smem)) return r;
-  if (int r = lg_func_smem_once((const void*)tc_attention_kernel<false>, smem)) return r;
-  if (h->cfg.precision == LG_PREC_BF16) tc_attention_kernel<true><<<grid, 384, smem, stream>>>(p);
-  else tc_attention_kernel<false><<<grid, 384, smem, stream>>>(p);
-  LG_CHECK_LAUNCH();
+  constexpr int smem2 = 2 * Q_TILE_BYTES + B_KV_STAGES * B_STAGE_BYTES + 1024 + 256;
+  if (int r = lg_func_smem_once((const void*)tc_attention2_kernel, smem2)) return r;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute at[1];
+  cfg.gridDim = grid; cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem2; cfg.stream = stream;
+  if (tc_use_pdl()) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+  }
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, tc_attention2_kernel, p);
+  if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
   return 0;
 }
