@@ -262,11 +262,11 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
             if (X3) {
               tma_load_2d_cg2(sa, &p.a_hi[seg], kc, (int)ti.grow0, &full[stage]);
               tma_load_2d_cg2(sa + A_TILE_BYTES, &p.a_lo[seg], kc, (int)ti.grow0, &full[stage]);
-              tma_load_3d_cg2(sa + 2 * A_TILE_BYTES, &p.w_hi_half, kb * BK, wrow, 0, &full[stage]);
-              tma_load_3d_cg2(sa + 2 * A_TILE_BYTES + C::W_PART, &p.w_lo_half, kb * BK, wrow, 0, &full[stage]);
+              tma_load_3d_cg2(sa + 2 * A_TILE_BYTES, &p.w_hi_half, kb * BK, wrow, ti.sel, &full[stage]);
+              tma_load_3d_cg2(sa + 2 * A_TILE_BYTES + C::W_PART, &p.w_lo_half, kb * BK, wrow, ti.sel, &full[stage]);
             } else {
               tma_load_2d_cg2(sa, &p.a_hi[seg], kc, (int)ti.grow0, &full[stage]);
-              tma_load_3d_cg2(sa + A_TILE_BYTES, &p.w_hi_half, kb * BK, wrow, 0, &full[stage]);
+              tma_load_3d_cg2(sa + A_TILE_BYTES, &p.w_hi_half, kb * BK, wrow, ti.sel, &full[stage]);
             }
           } else {
             const int pass = it / p.kb_total, kb = it % p.kb_total;
@@ -525,16 +525,27 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
           const float var = fmaxf((m2 + dev * HCOLS) * (1.f / COLS), 0.f);
           rstd = rsqrtf(var + 1e-5f);
         }
+        // residual row segments (x + ffn(...), lightglue.py:172 / 228-229) are fetched one chunk ahead: the load of
+        // chunk c + 1 is in flight while chunk c is processed (its HBM latency was the top stall of this epilogue)
+        float4 xr[8], xn[8];
+        if (NSLOT == 1 && EPI == TEPI_RESID) {
+          const float4* xp = reinterpret_cast<const float4*>(p.out_f32 + grow * p.ldo + ti.n_tile * COLS + half * HCOLS);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) xn[j4] = xp[j4];
+        }
         for (int c0 = 0; c0 < HCOLS; c0 += 32) {
           const int ci = c0 / 32;                      // chunk index inside this warp's half
           const int tcol = half * HCOLS + c0;          // column inside the tile
           const int col = ti.n_tile * COLS + tcol;     // output channel of element 0 of this chunk
           tmem_ld32(tl + c0, raw);
-          float4 xr[8];
-          if (NSLOT == 1 && EPI == TEPI_RESID) {     // residual row segment (x + ffn(...), lightglue.py:172 / 228-229)
-            const float4* xp = reinterpret_cast<const float4*>(p.out_f32 + grow * p.ldo + col);
+          if (NSLOT == 1 && EPI == TEPI_RESID) {
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) xr[j4] = xp[j4];
+            for (int j4 = 0; j4 < 8; ++j4) xr[j4] = xn[j4];
+            if (c0 + 32 < HCOLS) {
+              const float4* xp = reinterpret_cast<const float4*>(p.out_f32 + grow * p.ldo + col + 32);
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) xn[j4] = xp[j4];
+            }
           }
           if (lane == 0) tma_store_wait_read();        // every box of this warp may be rewritten
           tmem_ld_wait();
@@ -877,15 +888,17 @@ int launch_linear_e(TcLinParams& p, int n_tiles, bool cg2, cudaStream_t stream) 
 }
 int launch_linear(TcLinParams& p, int n_tiles, cudaStream_t stream) {
   static const bool use_cg2 = !(getenv("LG_TC_NO_CG2") && atoi(getenv("LG_TC_NO_CG2")) != 0);
-  const bool cg2 = use_cg2 && p.w_select == 0;  // per-tile W selection (final_proj heads, assignment sweeps) cannot share W
+  // per-pair weight selection (final_proj heads) cannot share W between the two row tiles of a CTA pair; the
+  // assignment sweeps can when both tiles belong to the same sequence (same partner): Lp a multiple of 256
+  const bool cg2 = use_cg2 && (p.w_select == 0 || (p.w_select == 2 && (p.st.Lp / BM) % 2 == 0));
   switch (p.epi) {
     case TEPI_QKV: return launch_linear_e<1, TEPI_QKV>(p, n_tiles, cg2, stream);
     case TEPI_BF16: return launch_linear_e<1, TEPI_BF16>(p, n_tiles, cg2, stream);
     case TEPI_LN_GELU: return launch_linear_e<2, TEPI_LN_GELU>(p, 1, cg2, stream);
     case TEPI_RESID: return launch_linear_e<1, TEPI_RESID>(p, n_tiles, cg2, stream);
     case TEPI_F32: return launch_linear_e<1, TEPI_F32>(p, n_tiles, cg2, stream);
-    case TEPI_LSE: return launch_linear_t<1, TEPI_LSE, false, false>(p, n_tiles, stream);
-    case TEPI_ARGMAX: return launch_linear_t<1, TEPI_ARGMAX, false, false>(p, n_tiles, stream);
+    case TEPI_LSE: return launch_linear_e<1, TEPI_LSE>(p, n_tiles, cg2, stream);
+    case TEPI_ARGMAX: return launch_linear_e<1, TEPI_ARGMAX>(p, n_tiles, cg2, stream);
   }
   return lg_set_error("launch_linear: bad epilogue");
 }
@@ -1000,6 +1013,9 @@ int tc_assign_sweeps(LgHandle* h, const TcBuffers& b, const SeqState& st, const 
     if ((r = wmap(h, &p.w_hi, b.msgh, st.Lp, LG_DIM, st.S, (uint64_t)st.Lp * LG_DIM))) return r;
     p.w_lo = p.w_hi;
     if (x3 && (r = wmap(h, &p.w_lo, b.msgl, st.Lp, LG_DIM, st.S, (uint64_t)st.Lp * LG_DIM))) return r;
+    if ((r = wmap(h, &p.w_hi_half, b.msgh, st.Lp, LG_DIM, st.S, (uint64_t)st.Lp * LG_DIM, BN / 2))) return r;
+    p.w_lo_half = p.w_hi_half;
+    if (x3 && (r = wmap(h, &p.w_lo_half, b.msgl, st.Lp, LG_DIM, st.S, (uint64_t)st.Lp * LG_DIM, BN / 2))) return r;
     p.kb0 = LG_DIM / BK; p.kb_total = LG_DIM / BK; p.passes = x3 ? 3 : 1;
     p.st = st; p.dbg = h->tc.dbg;
     h->launches += 1;

@@ -87,9 +87,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 // CTA pairs (cta_group::2): in the shared::cluster window bit 24 of a shared-memory address selects the CTA of the
 // pair; clearing it addresses the same offset in the even ("leader") CTA
 constexpr uint32_t PAIR_LEADER_MASK = 0xFEFFFFFFu;
-// arrive on the barrier at this offset in the LEADER CTA of the pair (from either CTA), release at cluster scope
+// arrive on the barrier at this offset in the LEADER CTA of the pair (from either CTA).  Plain arrive (no
+// cluster-scope release: that costs a MEMBAR + ERRBAR per arrival, 10-16 % of the epilogue's stall samples): what the
+// barrier orders here are TMEM reads against later MMAs, which the tcgen05 fences on both sides cover.
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PAIR_LEADER_MASK) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PAIR_LEADER_MASK) : "memory");
 }
 
 // ---------------------------------------------------------------- TMA
