@@ -34,6 +34,7 @@ struct AttnParams {
   __nv_bfloat16* ctxh; __nv_bfloat16* ctxl;
   int kv_shift;
   int rows_per_cta;  // 256 (two query tiles per CTA) or 128 (one: small problems that would not fill the SMs)
+  int pingpong;      // alternate the exponential phases of the CTA's two query tiles (LG_ATTN_NO_PINGPONG=1 switches it off)
   SeqState st;
   unsigned int* dbg;
 };
@@ -216,6 +217,8 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
         const uint32_t to = tmem_base + lane_off + 128 + t * 64;
         float m_used = -INFINITY, l = 0.f;
         uint32_t sv[2][32];
+        const bool pingpong = nt == 2 && p.pingpong;
+        if (pingpong && t == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");  // tile 0 goes first
         for (int j = 0; j < nkv; ++j) {
           mbar_wait_sleep(&s_full[t], j & 1, p.dbg, 6, j * 2 + t);
           tc_fence_after();
@@ -257,6 +260,14 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
             }
             l *= alpha;
           }
+          // Ping-pong between the two query tiles of the CTA (named barriers 2 / 3): the exponentials of tile t run
+          // while tile 1-t waits for its MMAs, and vice versa (measured on B200: 410 us per launch against 427 without).
+          // In-kernel clock trace of one tile at B=32, N=2048 (cycles per 64-key block, ~2900 in total): wait for S
+          // 580 (P arrival -> MMA warp wake 160, PV + next QK^T issue and execution behind the other tiles' MMAs
+          // 480), TMEM load 155, row max (+ lazy rescale) 430-780, exponentials 880-1100 (512 alone: the MUFU unit of
+          // a scheduler is shared by four tiles), P store + arrive 190.  Tried and measured slower: 32-key blocks
+          // with double-buffered S (473 us: the per-block fixed costs double).
+          if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(2 + t) : "memory");
           // P = exp2(c s - c m): the scale-and-shift and the row sum run as packed f32x2 operations
           const uint64_t sc2 = pack2(SCALE_LOG2, SCALE_LOG2);
           const float nmc = -m_used * SCALE_LOG2;
@@ -279,6 +290,7 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
             }
             tmem_st16(ts + c * 16, pk);
           }
+          if (pingpong && !(t == 1 && j + 1 == nkv)) asm volatile("bar.arrive %0, 256;" ::"r"(3 - t) : "memory");  // the other tile's turn
           {
             float a0, a1;
             unpack2(add2(la, lb), a0, a1);
@@ -352,6 +364,8 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
   p.ctxh = b.ctxh; p.ctxl = b.ctxl; p.kv_shift = kv_shift; p.st = st; p.dbg = h->tc.dbg;
   dim3 grid((st.Lp + 2 * QT - 1) / (2 * QT), LG_HEADS, st.S);
   p.rows_per_cta = 2 * QT;
+  static const bool no_pp = getenv("LG_ATTN_NO_PINGPONG") && atoi(getenv("LG_ATTN_NO_PINGPONG")) != 0;
+  p.pingpong = no_pp ? 0 : 1;
   if ((long)grid.x * grid.y * grid.z < 2 * lg_num_sms()) {  // fewer CTAs than resident slots: one query tile per CTA instead
     p.rows_per_cta = QT;
     grid.x = st.Lp / QT;
