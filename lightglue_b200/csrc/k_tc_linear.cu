@@ -79,7 +79,9 @@ struct TcLinParams {
 template <int NSLOT, bool CG2, bool X3>
 struct LinCfg {
   static_assert(CG2 || !X3, "the K-outer split staging exists in the CTA-pair kernels only");
-  static constexpr int NBUF = NSLOT == 1 ? 2 : 1;
+  // accumulator hand-over barriers: NSLOT == 1: two 256-column buffers used by alternate tiles; NSLOT == 2 (LayerNorm):
+  // the two 256-column SLOTS of one tile, completed and released one after the other
+  static constexpr int NBUF = 2;
   // epilogue warps: 8 (two per TMEM lane quarter, 128 columns each); the LayerNorm variant (512 columns, the
   // instruction-heaviest epilogue) runs 16 so that four warps per scheduler hide its latencies
   static constexpr int EW = NSLOT == 1 ? 8 : 16;
@@ -96,7 +98,7 @@ struct LinCfg {
   static constexpr int BOXB_OFF = NSLOT == 1 ? 4096 : 0;
   static constexpr int BOXC_OFF = NSLOT == 1 ? 8192 : 0;
   static constexpr int VEC_BYTES = (NSLOT == 1 ? 1 : 3) * COLS * 4;     // bias (| ln gamma | ln beta)
-  static constexpr int LNP_BYTES = NSLOT == 1 ? 0 : 128 * GROUPS * 8;    // LayerNorm partial (mean, M2) per row per column group
+  static constexpr int LNP_BYTES = NSLOT == 1 ? 0 : 128 * GROUPS * 2 * 8;  // LayerNorm partial (mean, M2) per row, slot and column group
   static constexpr int FIXED_BYTES = EW * WARP_BYTES + VEC_BYTES + LNP_BYTES + 512 + 1024;
   static constexpr int SMEM_MAX = 232448;  // 227 KB per CTA
   static constexpr int FIT = (SMEM_MAX - FIXED_BYTES) / STAGE_BYTES;
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
           if (CG2) {
             // pair mode: this CTA's A rows and its half (128 of 256 rows) of the W tile; the bytes of BOTH CTAs complete
             // on the leader's barrier, which only the leader arms
-            const int kb = it / NSLOT, sl_ = it % NSLOT;
+            const int sl_ = it / p.kb_total, kb = it % p.kb_total;  // slot outermost: slot 0 completes (and is normalised) first
             const int seg = kb >= p.kb0 ? 1 : 0;
             const int kc = (seg ? kb - p.kb0 : kb) * BK;
             const int wrow = (ti.n_tile * NSLOT + sl_) * BN + rank * (BN / 2);
@@ -293,20 +295,30 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
     TileInfo ti;
     bool store;
     while ((!CG2 || rank == 0) && walk.next(p, ti, store)) {  // pair mode: the leader issues for both CTAs
-      const int buf = li % NBUF;
-      // the epilogue warps (pair mode: of both CTAs) have drained this accumulator
-      if (CG2) mbar_wait_cluster(&acc_empty[buf], ((li / NBUF) & 1) ^ 1, p.dbg, 20, li);
-      else mbar_wait(&acc_empty[buf], ((li / NBUF) & 1) ^ 1, p.dbg, 20, li);
-      tc_fence_after();
+      const int buf = NSLOT == 1 ? li % NBUF : 0;
+      const uint32_t par = NSLOT == 1 ? (uint32_t)((li / NBUF) & 1) : (uint32_t)(li & 1);
+      // the epilogue warps (pair mode: of both CTAs) have drained this accumulator; the LayerNorm variant waits per
+      // slot, right before the slot's first MMA, so that slot 0 of the next tile overlaps the normalisation of slot 1
+      if (NSLOT == 1 || !CG2) {
+        for (int bb = 0; bb < (NSLOT == 1 ? 1 : 2); ++bb) {
+          if (CG2) mbar_wait_cluster(&acc_empty[buf + bb], par ^ 1, p.dbg, 20, li);
+          else mbar_wait(&acc_empty[buf + bb], par ^ 1, p.dbg, 20, li);
+        }
+        tc_fence_after();
+      }
       const uint32_t acc = tmem_base + buf * BN;
       for (int it = 0; it < iters; ++it, ++g) {
         const int stage = g % STAGES, round = g / STAGES;
+        if (NSLOT == 2 && CG2 && it % p.kb_total == 0) {
+          mbar_wait_cluster(&acc_empty[it / p.kb_total], par ^ 1, p.dbg, 20, li);
+          tc_fence_after();
+        }
         mbar_wait(&full[stage], round & 1, p.dbg, 18, it);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           if (CG2) {
-            const int kb = it / NSLOT, sl_ = it % NSLOT;
+            const int sl_ = it / p.kb_total, kb = it % p.kb_total;
             const uint32_t d = acc + sl_ * BN;
             if (X3) {
               const uint64_t ahi = make_sdesc_sw128(sa), alo = make_sdesc_sw128(sa + A_TILE_BYTES);
@@ -323,7 +335,7 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
               for (int k = 0; k < BK / 16; ++k) mma_ss_cg2(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
             mma_commit_cg2(&empty[stage], (uint16_t)3);  // frees the stage in both CTAs
-            if (it == iters - 1) mma_commit_cg2(&acc_full[buf], (uint16_t)3);
+            if (kb == p.kb_total - 1) mma_commit_cg2(&acc_full[buf + sl_], (uint16_t)3);  // this 256-column accumulator is complete
           } else {
             const uint64_t adesc = make_sdesc_sw128(sa);
 #pragma unroll
@@ -334,7 +346,10 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
                 mma_ss(acc + sl_ * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
             }
             mma_commit(&empty[stage]);
-            if (it == iters - 1) mma_commit(&acc_full[buf]);
+            if (it == iters - 1) {
+              mma_commit(&acc_full[buf]);
+              if (NSLOT == 2) mma_commit(&acc_full[1]);
+            }
           }
         }
         __syncwarp();
@@ -367,13 +382,19 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
     TileInfo ti;
     bool store;
     while (walk.next(p, ti, store)) {
-      const int buf = li % NBUF;
-      if (!store) {  // dead tile of a live pair (only in cluster mode): drain the accumulator, write nothing
-        mbar_wait(&acc_full[buf], (li / NBUF) & 1, p.dbg, 23, li);
-        tc_fence_after();
+      const int buf = NSLOT == 1 ? li % NBUF : 0;
+      const uint32_t par = NSLOT == 1 ? (uint32_t)((li / NBUF) & 1) : (uint32_t)(li & 1);
+      auto release_acc = [&](int bb) {  // this warp has finished reading accumulator bb
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if (CG2) mbar_arrive_leader(&acc_empty[buf]); else mbar_arrive(&acc_empty[buf]); }
+        if (lane == 0) { if (CG2) mbar_arrive_leader(&acc_empty[bb]); else mbar_arrive(&acc_empty[bb]); }
+      };
+      if (!store) {  // dead tile of a live pair (only in cluster mode): drain the accumulator(s), write nothing
+        for (int bb = 0; bb < (NSLOT == 1 ? 1 : 2); ++bb) {
+          mbar_wait(&acc_full[buf + bb], par, p.dbg, 23, li);
+          tc_fence_after();
+          release_acc(buf + bb);
+        }
         ++li;
         continue;
       }
@@ -394,7 +415,115 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
       if (!is_sweep)
         for (int i = te; i < COLS; i += EPI_WARPS * 32) s_bias[i] = bias[i];
       epi_bar();
-      mbar_wait(&acc_full[buf], (li / NBUF) & 1, p.dbg, 19, li);
+      if (EPI == TEPI_LN_GELU) {
+        // ---------------------------------------------------------------- LayerNorm(512) + GELU, slot by slot
+        // Warp (quarter, group g) owns rows 32 quarter .. +31 and columns 64 g .. +63 of BOTH 256-column slots.
+        // Statistics of slot 0 are taken while the tensor core still works on slot 1; after the merge slot 0 is
+        // normalised and handed back first, so the MMAs of the next tile's slot 0 overlap the normalisation of slot 1.
+        constexpr int GC = 64;
+        const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        uint32_t raw[32];
+        for (int sl = 0; sl < 2; ++sl) {
+          mbar_wait(&acc_full[sl], par, p.dbg, 19, li);
+          tc_fence_after();
+          float sh = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int c0 = 0; c0 < GC; c0 += 32) {
+            const int tcol = sl * BN + half * GC + c0;
+            tmem_ld32(tq + tcol, raw);
+            tmem_ld_wait();
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + tcol);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = b4[j4];
+              const float v0 = __uint_as_float(raw[4 * j4]) + bb.x, v1 = __uint_as_float(raw[4 * j4 + 1]) + bb.y;
+              const float v2 = __uint_as_float(raw[4 * j4 + 2]) + bb.z, v3 = __uint_as_float(raw[4 * j4 + 3]) + bb.w;
+              if (c0 == 0 && j4 == 0) sh = v0;  // shift by the first element: cancellation-free E[(v-sh)^2]
+              const float d0 = v0 - sh, d1 = v1 - sh, d2 = v2 - sh, d3 = v3 - sh;
+              s1 += (d0 + d1) + (d2 + d3);
+              s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
+            }
+          }
+          // this group: mean_g = sh + s1/GC, M2_g = sum (v - mean_g)^2 = s2 - s1^2/GC (shifted -> no cancellation)
+          s_lnp[(sl * C::GROUPS + half) * 128 + quarter * 32 + lane] = make_float2(sh + s1 * (1.f / GC), s2 - s1 * s1 * (1.f / GC));
+        }
+        epi_bar();
+        // equal-sized groups merge with Chan's formula: mean = avg(mean_g), M2 = sum M2_g + GC * sum (mean_g - mean)^2
+        float msum = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int g = 0; g < 2 * C::GROUPS; ++g) { const float2 a = s_lnp[g * 128 + quarter * 32 + lane]; msum += a.x; m2 += a.y; }
+        const float mean = msum * (1.f / (2 * C::GROUPS));
+        float dev = 0.f;
+#pragma unroll
+        for (int g = 0; g < 2 * C::GROUPS; ++g) { const float dm = s_lnp[g * 128 + quarter * 32 + lane].x - mean; dev = fmaf(dm, dm, dev); }
+        const float rstd = rsqrtf(fmaxf((m2 + dev * GC) * (1.f / COLS), 0.f) + 1e-5f);
+        const bool haslo = p.out_l != nullptr;
+        uint8_t* box = epi_smem + ew * C::WARP_BYTES;  // one dense 32 x 32 bf16 box per warp (hi, then lo)
+        uint8_t* brow32 = box + lane * 64;
+        const int grow_w2 = (int)ti.grow0 + quarter * 32;
+        for (int sl = 0; sl < 2; ++sl) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < GC; c0 += 32) {
+            const int tcol = sl * BN + half * GC + c0;
+            tmem_ld32(tq + tcol, raw);
+            if (lane == 0) tma_store_wait_read();        // the box may be rewritten
+            tmem_ld_wait();
+            __syncwarp();
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + tcol);
+            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + tcol);
+            const float4* e4 = reinterpret_cast<const float4*>(s_beta + tcol);
+            float v[32];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = b4[j4], g = g4[j4], be = e4[j4];
+              const float xin[4] = {__uint_as_float(raw[4 * j4]) + bb.x, __uint_as_float(raw[4 * j4 + 1]) + bb.y,
+                                    __uint_as_float(raw[4 * j4 + 2]) + bb.z, __uint_as_float(raw[4 * j4 + 3]) + bb.w};
+              const float gg[4] = {g.x, g.y, g.z, g.w}, bt[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float y = fmaf((xin[e] - mean) * rstd, gg[e], bt[e]);
+                // exact (erf) GELU; erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): 1 MUFU.RCP + 1 MUFU.EX2
+                const float z = fabsf(y) * 0.70710678118654752f;
+                const float tt = rcp_approx(fmaf(0.3275911f, z, 1.f));
+                float pl = fmaf(1.061405429f, tt, -1.453152027f);
+                pl = fmaf(pl, tt, 1.421413741f); pl = fmaf(pl, tt, -0.284496736f); pl = fmaf(pl, tt, 0.254829592f);
+                const float ez = ex2_approx(-1.4426950408889634f * z * z);
+                const float erf_abs = fmaf(-pl * tt, ez, 1.f);
+                const float hy = 0.5f * y;
+                v[4 * j4 + e] = fmaf(copysignf(erf_abs, y), hy, hy);
+              }
+            }
+            for (int pass = 0; pass < (haslo ? 2 : 1); ++pass) {
+              if (pass == 1) {
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+              }
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a = v[8 * j8 + 2 * e], b = v[8 * j8 + 2 * e + 1];
+                  const uint32_t hi = pack_bf16x2(a, b);
+                  w[e] = pass == 0 ? hi : pack_bf16x2_lo(a, b, hi);
+                }
+                *reinterpret_cast<uint4*>(brow32 + (j8 << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(pass == 0 ? &p.o_h32 : &p.o_l32, box, tcol, grow_w2);
+                tma_store_commit();
+              }
+            }
+            __syncwarp();
+          }
+          release_acc(sl);  // slot sl of this tile is drained: the next tile's MMAs may overwrite it
+        }
+        ++li;
+        continue;
+      }
+      mbar_wait(&acc_full[buf], par, p.dbg, 19, li);
       tc_fence_after();
       const uint32_t tl = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16) + half * HCOLS;
       const int r = ti.r0 + row;
@@ -490,41 +619,6 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
           }
         }
       } else {
-        float mean = 0.f, rstd = 1.f;
-        if (EPI == TEPI_LN_GELU) {
-          // LayerNorm(512, eps 1e-5) statistics (lightglue.py:154): shifted single sweep over this warp's half
-          // of the row, halves merged through shared memory
-          float sh = 0.f, s1 = 0.f, s2 = 0.f;
-          for (int c0 = 0; c0 < HCOLS; c0 += 32) {
-            tmem_ld32(tl + c0, raw);
-            tmem_ld_wait();
-            const float4* b4 = reinterpret_cast<const float4*>(s_bias + half * HCOLS + c0);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bb = b4[j4];
-              const float v0 = __uint_as_float(raw[4 * j4]) + bb.x, v1 = __uint_as_float(raw[4 * j4 + 1]) + bb.y;
-              const float v2 = __uint_as_float(raw[4 * j4 + 2]) + bb.z, v3 = __uint_as_float(raw[4 * j4 + 3]) + bb.w;
-              if (c0 == 0 && j4 == 0) sh = v0;  // shift by the first element: cancellation-free E[(v-sh)^2]
-              const float d0 = v0 - sh, d1 = v1 - sh, d2 = v2 - sh, d3 = v3 - sh;
-              s1 += (d0 + d1) + (d2 + d3);
-              s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
-            }
-          }
-          // this group: mean_g = sh + s1/H, M2_g = sum (v - mean_g)^2 = s2 - s1^2/H (shifted -> no cancellation);
-          // equal-sized groups merge with Chan's formula: mean = avg(mean_g), M2 = sum M2_g + H * sum (mean_g - mean)^2
-          const float mh = sh + s1 * (1.f / HCOLS);
-          s_lnp[half * 128 + row] = make_float2(mh, s2 - s1 * s1 * (1.f / HCOLS));
-          epi_bar();
-          float msum = 0.f, m2 = 0.f;
-#pragma unroll
-          for (int g = 0; g < C::GROUPS; ++g) { const float2 a = s_lnp[g * 128 + row]; msum += a.x; m2 += a.y; }
-          mean = msum * (1.f / C::GROUPS);
-          float dev = 0.f;
-#pragma unroll
-          for (int g = 0; g < C::GROUPS; ++g) { const float dm = s_lnp[g * 128 + row].x - mean; dev = fmaf(dm, dm, dev); }
-          const float var = fmaxf((m2 + dev * HCOLS) * (1.f / COLS), 0.f);
-          rstd = rsqrtf(var + 1e-5f);
-        }
         // residual row segments (x + ffn(...), lightglue.py:172 / 228-229) are fetched one chunk ahead: the load of
         // chunk c + 1 is in flight while chunk c is processed (its HBM latency was the top stall of this epilogue)
         float4 xr[8], xn[8];
@@ -568,28 +662,7 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
             }
             continue;
           }
-          if (EPI == TEPI_LN_GELU) {
-            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + tcol);
-            const float4* e4 = reinterpret_cast<const float4*>(s_beta + tcol);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 g = g4[j4], be = e4[j4];
-              const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {be.x, be.y, be.z, be.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float y = fmaf((v[4 * j4 + e] - mean) * rstd, gg[e], bb[e]);
-                // exact (erf) GELU; erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): 1 MUFU.RCP + 1 MUFU.EX2
-                const float z = fabsf(y) * 0.70710678118654752f;
-                const float tt = rcp_approx(fmaf(0.3275911f, z, 1.f));
-                float pl = fmaf(1.061405429f, tt, -1.453152027f);
-                pl = fmaf(pl, tt, 1.421413741f); pl = fmaf(pl, tt, -0.284496736f); pl = fmaf(pl, tt, 0.254829592f);
-                const float ez = ex2_approx(-1.4426950408889634f * z * z);
-                const float erf_abs = fmaf(-pl * tt, ez, 1.f);
-                const float hy = 0.5f * y;
-                v[4 * j4 + e] = fmaf(copysignf(erf_abs, y), hy, hy);
-              }
-            }
-          } else if (p.scale != 1.f) {
+          if (p.scale != 1.f) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= p.scale;
           }
@@ -619,41 +692,13 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
           }
           const bool f32out = NSLOT == 1 && (EPI == TEPI_RESID || EPI == TEPI_F32);
           const bool fp16 = EPI == TEPI_QKV;
-          const bool has16 = fp16 || EPI == TEPI_BF16 || EPI == TEPI_LN_GELU || EPI == TEPI_RESID ||
+          const bool has16 = fp16 || EPI == TEPI_BF16 || EPI == TEPI_RESID ||
                              (EPI == TEPI_F32 && p.out_h != nullptr);
           const bool haslo = has16 && !fp16 && p.out_l != nullptr;
           if (f32out) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4)
               *reinterpret_cast<float4*>(arow + ((j4 ^ sw) << 4)) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-          }
-          if (NSLOT == 2) {
-            // LayerNorm variant: one dense 32 x 32 bf16 box per warp; hi leaves first, then (bf16x3) lo through the same box
-            for (int pass = 0; pass < (haslo ? 2 : 1); ++pass) {
-              if (pass == 1) {
-                if (lane == 0) tma_store_wait_read();
-                __syncwarp();
-              }
-#pragma unroll
-              for (int j8 = 0; j8 < 4; ++j8) {
-                uint32_t w[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float a = v[8 * j8 + 2 * e], b = v[8 * j8 + 2 * e + 1];
-                  const uint32_t hi = pack_bf16x2(a, b);
-                  w[e] = pass == 0 ? hi : pack_bf16x2_lo(a, b, hi);
-                }
-                *reinterpret_cast<uint4*>(crow_lo + (j8 << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-              }
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(pass == 0 ? &p.o_h32 : &p.o_l32, boxC, col, grow_w);
-                tma_store_commit();
-              }
-            }
-            __syncwarp();
-            continue;
           }
           if (has16) {
 #pragma unroll
@@ -690,9 +735,7 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
         }
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { if (CG2) mbar_arrive_leader(&acc_empty[buf]); else mbar_arrive(&acc_empty[buf]); }
+      release_acc(buf);
       ++li;
     }
     if (lane == 0) tma_store_wait_all();
