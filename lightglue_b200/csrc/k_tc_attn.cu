@@ -266,7 +266,9 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
           // 580 (P arrival -> MMA warp wake 160, PV + next QK^T issue and execution behind the other tiles' MMAs
           // 480), TMEM load 155, row max (+ lazy rescale) 430-780, exponentials 880-1100 (512 alone: the MUFU unit of
           // a scheduler is shared by four tiles), P store + arrive 190.  Tried and measured slower: 32-key blocks
-          // with double-buffered S (473 us: the per-block fixed costs double).
+          // with double-buffered S (473 us: the per-block fixed costs double); exponentials started speculatively
+          // against the previous reference maximum with the row maximum taken in the same loop (7.70 vs 7.50 ms of
+          // attention per step: redone blocks and the longer loop body cost more than the shorter chain saves).
           if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(2 + t) : "memory");
           // P = exp2(c s - c m): the scale-and-shift and the row sum run as packed f32x2 operations
           const uint64_t sc2 = pack2(SCALE_LOG2, SCALE_LOG2);

@@ -390,6 +390,8 @@ extern "C" size_t lg_workspace_bytes(const LgHandle* h, int32_t B, int32_t M, in
 static int run_assign(LgHandle* h, const Workspace& w, const SeqState& st, const float* x, const int* ind, int M, int N,
                       const LgOutputs* out, cudaStream_t stream) {
   const float* abase = h->wpk + h->o_assign;
+  // the whole materialising stage (final_proj + both sweeps + combines + dustbin + filter + output) as one interval
+  Timer tstage(h, LG_K_ASSIGN_STAGE, stream, out->log_assignment != nullptr);
   {
     Timer t(h, LG_K_LINEAR, stream);
     if (h->cfg.precision == LG_PREC_FP32) {
