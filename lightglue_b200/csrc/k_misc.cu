@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(256) posenc_kernel(PosencArgs a) {
   const float shx = sz[0] / 2.f, shy = sz[1] / 2.f, scale = fmaxf(sz[0], sz[1]) / 2.f;  // (40-41)
   float* out = a.cs + (long)s * a.Lp * 64;
   (void)S;
-  for (int e = tid; e < n * 32; e += 256) {
+  // the rows of a sequence are spread over gridDim.y CTAs (each repeats the cheap bounding-box reduction above)
+  for (int e = blockIdx.y * 256 + tid; e < n * 32; e += 256 * gridDim.y) {
     const int i = e / 32, f = e % 32;
     const float x = (kp[i * 2] - shx) / scale, y = (kp[i * 2 + 1] - shy) / scale;  // (42)
     const float* w = a.wr + f * a.pos_dim;
@@ -67,13 +68,18 @@ __global__ void __launch_bounds__(256) posenc_kernel(PosencArgs a) {
 }
 
 int misc_posenc(const PosencArgs& a, cudaStream_t stream) {
-  posenc_kernel<<<2 * a.B, 256, 0, stream>>>(a);
+  const int mx = a.M > a.N ? a.M : a.N;
+  int chunks = (mx * 32 + 256 * 16 - 1) / (256 * 16);  // ~16 encodings per thread
+  if (chunks < 1) chunks = 1;
+  if (chunks > 64) chunks = 64;
+  posenc_kernel<<<dim3(2 * a.B, chunks), 256, 0, stream>>>(a);
   LG_CHECK_LAUNCH();
   return 0;
 }
 
 __global__ void pack_desc_kernel(const float* __restrict__ d0, const float* __restrict__ d1, float* __restrict__ out, int B,
-                                 int M, int N, int Lp, int d, const int* __restrict__ lens0, const int* __restrict__ lens1) {
+                                 int M, int N, int Lp, int d, const int* __restrict__ lens0, const int* __restrict__ lens1,
+                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   const int s = blockIdx.y, r = blockIdx.x;
   const bool im1 = s >= B;
   const int* lens = im1 ? lens1 : lens0;
@@ -81,15 +87,30 @@ __global__ void pack_desc_kernel(const float* __restrict__ d0, const float* __re
   if (r >= n) return;
   const float* src = (im1 ? d1 + ((long)(s - B) * N + r) * d : d0 + ((long)s * M + r) * d);
   float* dst = out + ((long)s * Lp + r) * d;
-  for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4)
-    *reinterpret_cast<float4*>(dst + c) = *reinterpret_cast<const float4*>(src + c);
+  for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
+    const float4 t = *reinterpret_cast<const float4*>(src + c);
+    *reinterpret_cast<float4*>(dst + c) = t;
+    if (hi) {  // bf16 hi (/ lo) images for the tensor-core linears, written in the same pass
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(t.x, t.y), h1 = __floats2bfloat162_rn(t.z, t.w);
+      const long o = ((long)s * Lp + r) * d + c;
+      *reinterpret_cast<__nv_bfloat162*>(hi + o) = h0;
+      *reinterpret_cast<__nv_bfloat162*>(hi + o + 2) = h1;
+      if (lo) {
+        *reinterpret_cast<__nv_bfloat162*>(lo + o) =
+            __floats2bfloat162_rn(t.x - __bfloat162float(h0.x), t.y - __bfloat162float(h0.y));
+        *reinterpret_cast<__nv_bfloat162*>(lo + o + 2) =
+            __floats2bfloat162_rn(t.z - __bfloat162float(h1.x), t.w - __bfloat162float(h1.y));
+      }
+    }
+  }
 }
 
 int misc_pack_desc(const float* d0, const float* d1, float* out, int B, int M, int N, int Lp, int d, const int* lens0,
-                   const int* lens1, cudaStream_t stream) {
+                   const int* lens1, cudaStream_t stream, void* hi, void* lo) {
   const int mx = M > N ? M : N;
   if (mx == 0) return 0;
-  pack_desc_kernel<<<dim3(mx, 2 * B), 64, 0, stream>>>(d0, d1, out, B, M, N, Lp, d, lens0, lens1);
+  pack_desc_kernel<<<dim3(mx, 2 * B), 64, 0, stream>>>(d0, d1, out, B, M, N, Lp, d, lens0, lens1, (__nv_bfloat16*)hi,
+                                                       (__nv_bfloat16*)lo);
   LG_CHECK_LAUNCH();
   return 0;
 }

@@ -931,9 +931,9 @@ int launch_linear_e(TcLinParams& p, int n_tiles, bool cg2, cudaStream_t stream) 
 }
 int launch_linear(TcLinParams& p, int n_tiles, cudaStream_t stream) {
   static const bool use_cg2 = !(getenv("LG_TC_NO_CG2") && atoi(getenv("LG_TC_NO_CG2")) != 0);
-  // per-pair weight selection (final_proj heads) cannot share W between the two row tiles of a CTA pair; the
-  // assignment sweeps can when both tiles belong to the same sequence (same partner): Lp a multiple of 256
-  const bool cg2 = use_cg2 && (p.w_select == 0 || (p.w_select == 2 && (p.st.Lp / BM) % 2 == 0));
+  // per-tile weight selection (final_proj head of the pair's exit layer; the partner's descriptors in the assignment
+  // sweeps): the two row tiles of a CTA pair share W only when both belong to the same sequence, i.e. Lp % 256 == 0
+  const bool cg2 = use_cg2 && (p.w_select == 0 || (p.st.Lp / BM) % 2 == 0);
   switch (p.epi) {
     case TEPI_QKV: return launch_linear_e<1, TEPI_QKV>(p, n_tiles, cg2, stream);
     case TEPI_BF16: return launch_linear_e<1, TEPI_BF16>(p, n_tiles, cg2, stream);
@@ -970,10 +970,10 @@ int run_linear(LgHandle* h, const SeqState& st, const LinDesc& d, TcLinParams& p
   if ((r = wmap(h, &p.w_hi, h->tc.w_hi + d.w_off, d.nout, K, d.nsel, d.sel_stride))) return r;
   p.w_lo = p.w_hi;
   if (x3 && (r = wmap(h, &p.w_lo, h->tc.w_lo + d.w_off, d.nout, K, d.nsel, d.sel_stride))) return r;
-  if (d.nsel == 1) {  // half-height boxes for the multicast path
-    if ((r = wmap(h, &p.w_hi_half, h->tc.w_hi + d.w_off, d.nout, K, 1, 0, BN / 2))) return r;
+  {  // half-height boxes: each CTA of a pair holds 128 of the 256 rows of a W tile
+    if ((r = wmap(h, &p.w_hi_half, h->tc.w_hi + d.w_off, d.nout, K, d.nsel, d.sel_stride, BN / 2))) return r;
     p.w_lo_half = p.w_hi_half;
-    if (x3 && (r = wmap(h, &p.w_lo_half, h->tc.w_lo + d.w_off, d.nout, K, 1, 0, BN / 2))) return r;
+    if (x3 && (r = wmap(h, &p.w_lo_half, h->tc.w_lo + d.w_off, d.nout, K, d.nsel, d.sel_stride, BN / 2))) return r;
   }
   if (p.out_h && (r = omap2d(h, &p.o_h, p.out_h, 2, p.ldb, rows, 64, true))) return r;
   if (p.out_l && (r = omap2d(h, &p.o_l32, p.out_l, 2, p.ldb, rows, 32, false))) return r;

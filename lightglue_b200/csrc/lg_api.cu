@@ -492,9 +492,9 @@ extern "C" int lg_forward(LgHandle* h, const LgInputs* in, const LgOutputs* out,
   }
   // descriptors -> residual stream (optionally through input_proj, lightglue.py:521-522)
   if (h->cfg.input_dim == (int)D) {
-    RC(misc_pack_desc(in->desc0, in->desc1, x, B, M, N, Lp, D, in->lens0, in->lens1, stream));
+    RC(misc_pack_desc(in->desc0, in->desc1, x, B, M, N, Lp, D, in->lens0, in->lens1, stream, fp32 ? nullptr : (void*)w.tc.xh,
+                      fp32 ? nullptr : (void*)w.tc.xl));
     h->launches += 1;
-    if (!fp32) { RC(tc_refresh_shadow(h, w.tc, x, st, stream)); h->launches += 1; }
   } else {
     RC(misc_pack_desc(in->desc0, in->desc1, w.hbuf, B, M, N, Lp, h->cfg.input_dim, in->lens0, in->lens1, stream));
     h->launches += 1;

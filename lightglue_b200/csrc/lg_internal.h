@@ -75,8 +75,9 @@ struct PosencArgs {
 };
 int misc_posenc(const PosencArgs& a, cudaStream_t stream);
 // descriptors [B,M,d] / [B,N,d] -> padded [S, Lp, d] fp32
+// (+ optionally the bf16 hi / lo images of the same rows, [S * Lp, d], for the tensor-core linears)
 int misc_pack_desc(const float* d0, const float* d1, float* out, int B, int M, int N, int Lp, int d, const int* lens0,
-                   const int* lens1, cudaStream_t stream);
+                   const int* lens1, cudaStream_t stream, void* hi = nullptr, void* lo = nullptr);
 // len[s] = lens[s] (or M / N), ind[s][r] = r, prune[s][r] = 1 for live rows, below = 0, stop_layer = 0 -- or 1 for a
 // pair with an empty image (answered like lightglue.py:568-588: no layer runs, nothing matches)
 int misc_init_state(int* len, int* ind, int* prune, int* stop_layer, int* below, int n_below, int B, int M, int N, int Lp,
