@@ -321,6 +321,10 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     from lightglue_b200 import LightGlue, synth
+    from lightglue_b200.sharding import bind_to_gpu_numa_node
+
+    # every rank runs next to its GPU: CPU affinity = the GPU's NUMA node, set BEFORE the pinned host buffers exist
+    numa = bind_to_gpu_numa_node(local_rank)
 
     B = args.batch
     sd = synth.make_state_dict()
@@ -355,18 +359,33 @@ def main():
         resolved before the next is enqueued (the reference's calling pattern).  Either way every step's result is
         resolved before the function returns.  N > 1: each step also gathers the match indices (int32 on the wire)."""
         prev, last = None, None
+        works, keep = [], []
         for _ in range(n_steps):
             cur = matcher.forward_async(resident)
             if world > 1:
-                wire = cur.tensors["matches0"].to(torch.int32)
-                buf = [torch.empty_like(wire) for _ in range(world)]
-                dist.all_gather(buf, wire)
+                # SURVEY 8e: the fixed-size results of every rank -- match indices of both images as int32 on the wire,
+                # both score tensors -- are gathered (2 collectives, 2 MB per rank); asynchronous, so the next
+                # forward's kernels are not serialised behind the collective
+                tt = cur.tensors
+                wi = torch.cat([tt["matches0"], tt["matches1"]], 1).to(torch.int32)
+                ws = torch.cat([tt["matching_scores0"], tt["matching_scores1"]], 1)
+                gi = torch.empty(world, *wi.shape, dtype=wi.dtype, device=dev)
+                gs = torch.empty(world, *ws.shape, dtype=ws.dtype, device=dev)
+                works.append(dist.all_gather_into_tensor(gi, wi, async_op=True))
+                works.append(dist.all_gather_into_tensor(gs, ws, async_op=True))
+                keep.append((gi, gs, wi, ws))
+                while len(works) > 4:
+                    works.pop(0).wait()
+                    if len(keep) > 3:
+                        keep.pop(0)
             if in_flight == 0:
                 last = cur.result()
                 continue
             if prev is not None:
                 last = prev.result()
             prev = cur
+        for w in works:
+            w.wait()
         return prev.result() if prev is not None else last
 
     # warm-up: W steps in each host calling pattern (also absorbs their one-time allocations), timed to pick the
@@ -552,7 +571,7 @@ def main():
                      " linears / fp16 attention operands / fp32 accumulate, softmax, LayerNorm, residual",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B, "keypoints": N_KPTS, "descriptor_dim": DESC,
-                       "layers": LAYERS, "precision": args.precision, "parallelism": f"pairs sharded over {world} GPU(s)",
+                       "layers": LAYERS, "precision": args.precision, "parallelism": f"pairs sharded over {world} GPU(s)", "numa_binding": numa,
                        "l2": "inputs (134 MB/step) + workspace (GBs) exceed the 126 MB L2; no explicit flush",
                        "host_pipelining": {"forwards_in_flight": in_flight, "warmup_ms_per_step_sync": mode_ms[0],
                                            "warmup_ms_per_step_one_in_flight": mode_ms[1],

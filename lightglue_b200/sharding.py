@@ -8,10 +8,60 @@ all; this module is the B200 deployment story for BASELINE conf
 """
 from __future__ import annotations
 
-from typing import Dict, List, Tuple
+import os
+from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(device_index: int) -> Optional[int]:
+    """NUMA node of a GPU from sysfs (``/sys/bus/pci/devices/<bdf>/numa_node``), or None when it cannot be told."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off (one process per GPU).
+
+    Pinned host buffers allocated AFTER this call are first-touched on that node, so the H2D / D2H copies of the
+    streaming path (``pipeline.match_stream``) do not cross the inter-socket link, and the threads that enqueue the
+    kernels run next to the GPU.  Without it the end-to-end throughput of a multi-rank job depends on where the
+    scheduler happened to place each rank (round 1: 0.62 of the resident rate at 2 ranks).  Returns what was done;
+    never raises (containers without sysfs topology simply stay unpinned)."""
+    info = {"device": device_index, "numa_node": None, "cpus": None, "bound": False}
+    node = gpu_numa_node(device_index)
+    if node is None:
+        return info
+    info["numa_node"] = node
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set(_parse_cpulist(f.read()))
+        allowed = set(os.sched_getaffinity(0))
+        use = sorted(cpus & allowed)
+        if use:
+            os.sched_setaffinity(0, use)
+            info["cpus"] = len(use)
+            info["bound"] = True
+    except Exception:
+        pass
+    return info
 
 
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:

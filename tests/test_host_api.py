@@ -153,3 +153,13 @@ def test_caller_glue_rbd_batch_to_device_match_pair():
     f0, f1, m01 = utils.match_pair(Extractor(), matcher, torch.zeros(1, 8, 5), torch.zeros(1, 8, 9), resize=512)
     assert f0["keypoints"].shape == (5, 2) and f1["descriptors"].shape == (9, 256) and f0["resize"] == 512
     assert m01["matches0"].shape == (5,) and m01["matches"].shape == (0, 2) and m01["stop"] == 3
+
+
+def test_numa_binding_helpers_never_raise():
+    """sharding.bind_to_gpu_numa_node: cpulist parsing, and a graceful no-op where there is no GPU / sysfs topology."""
+    from lightglue_b200 import sharding
+
+    assert sharding._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert sharding._parse_cpulist("") == []
+    info = sharding.bind_to_gpu_numa_node(0)
+    assert info["device"] == 0 and isinstance(info["bound"], bool)
