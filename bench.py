@@ -155,22 +155,33 @@ class CpuReference:
         self.threads = self.pick_threads()
 
     def pick_threads(self) -> int:
-        """torch's CPU path is not fastest at os.cpu_count() threads on a many-core host with a cgroup quota:
-        time the N=512 forward of THIS model for a few thread counts and keep the best (reported as `cores`)."""
+        """torch's CPU path is not fastest at os.cpu_count() threads on a many-core host with a cgroup quota, and one
+        N=2048 pair does not keep dozens of cores busy: time the N=512 forward of THIS model for a few (threads, pairs
+        per forward) combinations and keep the best pairs/s (reported as `cores` / `pairs_per_forward`)."""
         ncpu = host_cores()
         cands = sorted({c for c in (4, 8, 16, 32, 64) if c <= ncpu} | {ncpu})
-        best, best_t = ncpu, float("inf")
+        best, best_rate, best_b = ncpu, 0.0, 1
+        self.n512_ms = None
         with torch.no_grad():
-            for c in cands:
-                torch.set_num_threads(c)
-                self.fwd(self.small)
-                t0 = time.perf_counter()
-                self.fwd(self.small)
-                dt = time.perf_counter() - t0
-                if dt < best_t * 0.95:
-                    best, best_t = c, dt
+            for bsz in (1, 4):
+                d = self.small if bsz == 1 else {k: {kk: vv.expand(bsz, *vv.shape[1:]).contiguous() for kk, vv in v.items()}
+                                               for k, v in self.small.items()}
+                for c in cands:
+                    if bsz > 1 and c < 16:
+                        continue
+                    torch.set_num_threads(c)
+                    self.fwd(d)
+                    t0 = time.perf_counter()
+                    self.fwd(d)
+                    dt = time.perf_counter() - t0
+                    if bsz == 1 and (self.n512_ms is None or dt * 1e3 < self.n512_ms):
+                        self.n512_ms = dt * 1e3
+                    if bsz / dt > best_rate * 1.05:
+                        best, best_rate, best_b = c, bsz / dt, bsz
         torch.set_num_threads(best)
-        self.n512_ms = best_t * 1e3
+        self.pairs_per_forward = best_b
+        if best_b > 1:
+            self.data = {k: {kk: vv.expand(best_b, *vv.shape[1:]).contiguous() for kk, vv in v.items()} for k, v in self.data.items()}
         return best
 
     def run(self, n_pairs: int, budget_s: float = 1e9):
@@ -179,7 +190,7 @@ class CpuReference:
         with torch.no_grad():
             while done < n_pairs:
                 self.fwd(self.data)
-                done += 1
+                done += self.pairs_per_forward
                 if time.perf_counter() - t0 > budget_s:
                     break
         return done, time.perf_counter() - t0
@@ -187,7 +198,8 @@ class CpuReference:
     def describe(self, done, secs):
         return {"value": done / secs, "unit": "pairs/s", "cores": self.threads, "kind": self.kind,
                 "host_cores": host_cores(), "n512_ms_per_pair": round(self.n512_ms, 1),
-                "sample": f"{done} x 1 pair of the N=2048 workload ({secs:.1f} s), fp32, torch CPU, "
+                "pairs_per_forward": self.pairs_per_forward,
+                "sample": f"{done} pairs of the N=2048 workload, {self.pairs_per_forward} per forward ({secs:.1f} s), fp32, torch CPU, "
                           + ("unmodified reference lightglue.py" if self.kind == "reference" else "oracle port")}
 
 
@@ -213,7 +225,8 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": done, "warmup": min(args.warmup, 2), "ms_per_step": 1000.0 / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": "1 pair of the N=2048 workload per step, fp32, torch CPU"},
+        "config": {"workload": WORKLOAD, "sample": f"{cpu.pairs_per_forward} pair(s) of the N=2048 workload per step (one forward), "
+                                                     "fp32, torch CPU"},
         "cpu_baseline": cpu.describe(done, secs),
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -127,7 +127,7 @@ class LightGlue(nn.Module):
 
         self.static_lengths = None
         self.requires_grad_(False)
-        self._handle = None  # (C handle, device index, signature of the packed weights)
+        self._handle = None  # (C handle, signature: device index + precision / thresholds + identity of the packed weights)
         self._ws: Dict[tuple, torch.Tensor] = {}
         self._graphs: Dict[tuple, tuple] = {}
         self._meta_pool: Dict[int, list] = {}  # batch size -> free pinned [2, B] int32 read-back buffers
@@ -258,6 +258,13 @@ class LightGlue(nn.Module):
         says how many leading rows of that pair are real keypoints; the rest is padding that no kernel
         reads (the reference pads + masks instead, 46-55, 256-262, 512-520).  Padding rows come back as
         matches -1 / scores 0 / prune 0; every pair's result equals its own B=1 call.
+
+        Deviation from the reference for B > 1 with adaptive depth / width ON: early exit and point pruning are
+        decided PER PAIR on the device, and ``stop`` is the maximum over the batch.  The reference takes one
+        batch-global decision (the low-confidence count is summed over the batch and divided by one pair's m + n,
+        645-656; ``torch.where(mask)[1]`` concatenates the columns of all rows, 554/562), which is only well defined
+        for B == 1 -- there the results are identical (fixtures ``adaptive_*``).  With pruning / early exit off
+        (``depth_confidence = width_confidence = -1``) batched and single calls agree bit for bit.
         """
         for key in self.required_data_keys:
             assert key in data, f"Missing key {key} in data"
