@@ -22,7 +22,7 @@ extern "C" {
 #define LG_API __attribute__((visibility("default")))
 #endif
 
-#define SP_ABI_VERSION 1
+#define SP_ABI_VERSION 2
 
 /* Mirrors SuperPoint.default_conf (superpoint.py:112-118). */
 typedef struct SpConfig {
@@ -31,6 +31,9 @@ typedef struct SpConfig {
   int32_t max_num_keypoints;   /* conf.max_num_keypoints; <= 0 = None (no limit) */
   int32_t remove_borders;      /* conf.remove_borders (4) */
   float detection_threshold;   /* conf.detection_threshold (0.0005) */
+  int32_t precision;           /* arithmetic of the twelve convolutions (superpoint.py:137-153): 0 = fp32 on the CUDA
+                                  cores (the checker), 1 = tcgen05 tensor cores, split-bf16 operands (hi + lo, 3 MMAs per
+                                  product), fp32 accumulate */
 } SpConfig;
 
 typedef struct SpHandle SpHandle;

@@ -16,7 +16,7 @@ EXPORTS = (
     "lg_debug_timeout_code", "lg_debug_capture_layers", "lg_padded_length",
 )
 # include/superpoint_b200.h (same library)
-SP_ABI_VERSION = 1
+SP_ABI_VERSION = 2
 SP_EXPORTS = ("sp_weight_blob_floats", "sp_create", "sp_destroy", "sp_max_keypoints", "sp_workspace_bytes", "sp_forward")
 
 
@@ -31,7 +31,7 @@ class LgConfig(C.Structure):
 class SpConfig(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("nms_radius", C.c_int32), ("max_num_keypoints", C.c_int32),
-        ("remove_borders", C.c_int32), ("detection_threshold", C.c_float),
+        ("remove_borders", C.c_int32), ("detection_threshold", C.c_float), ("precision", C.c_int32),
     ]
 
 

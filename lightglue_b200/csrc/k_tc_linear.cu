@@ -28,7 +28,7 @@ constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int W_TILE_BYTES = BN * BK * 2;  // 32 KB
 
-enum { TEPI_QKV = 0, TEPI_BF16 = 1, TEPI_LN_GELU = 2, TEPI_RESID = 3, TEPI_F32 = 4, TEPI_LSE = 5, TEPI_ARGMAX = 6 };
+enum { TEPI_QKV = 0, TEPI_BF16 = 1, TEPI_LN_GELU = 2, TEPI_RESID = 3, TEPI_F32 = 4, TEPI_LSE = 5, TEPI_ARGMAX = 6, TEPI_CONV = 7 };
 
 struct TcLinParams {
   CUtensorMap a_hi[2], a_lo[2];  // A segment 0 / 1
@@ -49,6 +49,12 @@ struct TcLinParams {
   __half* q; __half* k; __half* vt; const float* cs;
   const float* ln_g; const float* ln_b;
   unsigned int* dbg;
+  // 3x3 convolution as a GEMM over a zero-padded NHWC image [rows = B (H+2) (W+2), Cin] (SuperPoint encoder): K block kb
+  // = (tap, 64-channel block); the A tile of a tap is the same matrix shifted by (dy (W+2) + dx) rows (TMA fills the
+  // rows outside the tensor with zeros).  conv_cb = Cin / 64 (0: not a convolution).  TEPI_CONV zeroes the padding
+  // pixels again on the way out (conv_w2 = W + 2, conv_plane = (H+2)(W+2), conv_rows = B conv_plane) and applies ReLU.
+  int conv_cb, conv_w2, conv_h, conv_w, relu;
+  long conv_plane, conv_rows;
   // epilogue tensor maps (all boxes are 32 rows x 128 bytes, 128B swizzle)
   CUtensorMap o_h;          // bf16 hi output [rows, ldb], box 64 cols x 32 rows, 128B swizzle (two chunks per store)
   CUtensorMap o_l32;        // bf16 lo output, box 32 cols x 32 rows, no swizzle (one chunk per store)
@@ -257,17 +263,24 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
             // pair mode: this CTA's A rows and its half (128 of 256 rows) of the W tile; the bytes of BOTH CTAs complete
             // on the leader's barrier, which only the leader arms
             const int sl_ = it / p.kb_total, kb = it % p.kb_total;  // slot outermost: slot 0 completes (and is normalised) first
-            const int seg = kb >= p.kb0 ? 1 : 0;
-            const int kc = (seg ? kb - p.kb0 : kb) * BK;
+            int seg = kb >= p.kb0 ? 1 : 0;
+            int kc = (seg ? kb - p.kb0 : kb) * BK;
+            int arow = (int)ti.grow0;
+            if (p.conv_cb) {  // convolution tap: shifted rows of the padded image, channel block kb % conv_cb
+              const int tap = kb / p.conv_cb;
+              arow += (tap / 3 - 1) * p.conv_w2 + (tap % 3 - 1);
+              kc = (kb % p.conv_cb) * BK;
+              seg = 0;
+            }
             const int wrow = (ti.n_tile * NSLOT + sl_) * BN + rank * (BN / 2);
             if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
             if (X3) {
-              tma_load_2d_cg2(sa, &p.a_hi[seg], kc, (int)ti.grow0, &full[stage]);
-              tma_load_2d_cg2(sa + A_TILE_BYTES, &p.a_lo[seg], kc, (int)ti.grow0, &full[stage]);
+              tma_load_2d_cg2(sa, &p.a_hi[seg], kc, arow, &full[stage]);
+              tma_load_2d_cg2(sa + A_TILE_BYTES, &p.a_lo[seg], kc, arow, &full[stage]);
               tma_load_3d_cg2(sa + 2 * A_TILE_BYTES, &p.w_hi_half, kb * BK, wrow, ti.sel, &full[stage]);
               tma_load_3d_cg2(sa + 2 * A_TILE_BYTES + C::W_PART, &p.w_lo_half, kb * BK, wrow, ti.sel, &full[stage]);
             } else {
-              tma_load_2d_cg2(sa, &p.a_hi[seg], kc, (int)ti.grow0, &full[stage]);
+              tma_load_2d_cg2(sa, &p.a_hi[seg], kc, arow, &full[stage]);
               tma_load_3d_cg2(sa + A_TILE_BYTES, &p.w_hi_half, kb * BK, wrow, ti.sel, &full[stage]);
             }
           } else {
@@ -275,10 +288,17 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
             // pass order (x3): A_lo*W_hi, A_hi*W_lo, A_hi*W_hi ; (bf16): A_hi*W_hi
             const bool a_lo = (p.passes == 3) && pass == 0;
             const bool w_lo = (p.passes == 3) && pass == 1;
-            const int seg = kb >= p.kb0 ? 1 : 0;
-            const int kc = (seg ? kb - p.kb0 : kb) * BK;
+            int seg = kb >= p.kb0 ? 1 : 0;
+            int kc = (seg ? kb - p.kb0 : kb) * BK;
+            int arow = (int)ti.grow0;
+            if (p.conv_cb) {
+              const int tap = kb / p.conv_cb;
+              arow += (tap / 3 - 1) * p.conv_w2 + (tap % 3 - 1);
+              kc = (kb % p.conv_cb) * BK;
+              seg = 0;
+            }
             mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-            tma_load_2d(sa, a_lo ? &p.a_lo[seg] : &p.a_hi[seg], kc, (int)ti.grow0, &full[stage]);
+            tma_load_2d(sa, a_lo ? &p.a_lo[seg] : &p.a_hi[seg], kc, arow, &full[stage]);
 #pragma unroll
             for (int sl_ = 0; sl_ < NSLOT; ++sl_)
               tma_load_3d(sa + A_TILE_BYTES + sl_ * W_TILE_BYTES, w_lo ? &p.w_lo : &p.w_hi, kb * BK,
@@ -631,6 +651,7 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
           const int ci = c0 / 32;                      // chunk index inside this warp's half
           const int tcol = half * HCOLS + c0;          // column inside the tile
           const int col = ti.n_tile * COLS + tcol;     // output channel of element 0 of this chunk
+          if (EPI == TEPI_CONV && col >= p.ldb) break; // Cout < 256: the weight rows beyond it are zero padding
           tmem_ld32(tl + c0, raw);
           if (NSLOT == 1 && EPI == TEPI_RESID) {
 #pragma unroll
@@ -666,6 +687,13 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= p.scale;
           }
+          if (EPI == TEPI_CONV) {  // ReLU, and the padding pixels of the NHWC image stay zero for the next layer's taps
+            const long pp = grow % p.conv_plane;
+            const int yy = (int)(pp / p.conv_w2), xx = (int)(pp % p.conv_w2);
+            const bool inside = grow < p.conv_rows && yy >= 1 && yy <= p.conv_h && xx >= 1 && xx <= p.conv_w;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = inside ? ((p.relu && v[j] < 0.f) ? 0.f : v[j]) : 0.f;
+          }
           if (NSLOT == 1 && EPI == TEPI_RESID) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
@@ -692,7 +720,7 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
           }
           const bool f32out = NSLOT == 1 && (EPI == TEPI_RESID || EPI == TEPI_F32);
           const bool fp16 = EPI == TEPI_QKV;
-          const bool has16 = fp16 || EPI == TEPI_BF16 || EPI == TEPI_RESID ||
+          const bool has16 = fp16 || EPI == TEPI_BF16 || EPI == TEPI_CONV || EPI == TEPI_RESID ||
                              (EPI == TEPI_F32 && p.out_h != nullptr);
           const bool haslo = has16 && !fp16 && p.out_l != nullptr;
           if (f32out) {
@@ -940,6 +968,7 @@ int launch_linear(TcLinParams& p, int n_tiles, cudaStream_t stream) {
     case TEPI_LN_GELU: return launch_linear_e<2, TEPI_LN_GELU>(p, 1, cg2, stream);
     case TEPI_RESID: return launch_linear_e<1, TEPI_RESID>(p, n_tiles, cg2, stream);
     case TEPI_F32: return launch_linear_e<1, TEPI_F32>(p, n_tiles, cg2, stream);
+    case TEPI_CONV: return launch_linear_e<1, TEPI_CONV>(p, n_tiles, cg2, stream);
     case TEPI_LSE: return launch_linear_e<1, TEPI_LSE>(p, n_tiles, cg2, stream);
     case TEPI_ARGMAX: return launch_linear_e<1, TEPI_ARGMAX>(p, n_tiles, cg2, stream);
   }
@@ -1167,6 +1196,43 @@ int tc_final_proj(LgHandle* h, const TcBuffers& b, const SeqState& st, float* p_
   p.out_f32 = p_out; p.ldo = LG_DIM; p.out_h = b.msgh; p.out_l = b.msgl; p.ldb = LG_DIM;  // bf16 images feed the sweeps
   LinDesc ld{b.xh, b.xl, LG_DIM, nullptr, nullptr, 0, h->o_assign + AO_FW, LG_DIM, h->cfg.n_layers, ASSIGN_BLOB_PAD};
   return run_linear(h, st, ld, p, stream);
+}
+
+int tc_conv(LgHandle* h, const SeqState& st, const __nv_bfloat16* in_h, const __nv_bfloat16* in_l, int cin, int taps, size_t w_off,
+            const float* bias, int relu, int B, int H, int W, __nv_bfloat16* out_h, __nv_bfloat16* out_l, int cout, float* out_f32,
+            int ldo, cudaStream_t stream) {
+  const bool x3 = h->cfg.precision == LG_PREC_BF16X3;
+  const uint64_t rows = (uint64_t)st.S * st.Lp;
+  const int K = taps * cin;
+  if (cin % BK != 0 || (taps != 1 && taps != 9)) return lg_set_error("tc_conv: Cin must be a multiple of 64, 1x1 or 3x3");
+  TcLinParams p{};
+  p.epi = out_f32 ? TEPI_F32 : TEPI_CONV;
+  p.scale = 1.f; p.bias = bias; p.relu = relu;
+  p.out_f32 = out_f32; p.ldo = ldo; p.out_h = out_h; p.out_l = x3 ? out_l : nullptr; p.ldb = cout;
+  int r;
+  if ((r = amap(h, &p.a_hi[0], in_h, rows, cin))) return r;
+  p.a_hi[1] = p.a_hi[0]; p.a_lo[0] = p.a_hi[0]; p.a_lo[1] = p.a_hi[0];
+  if (x3) { if ((r = amap(h, &p.a_lo[0], in_l, rows, cin))) return r; p.a_lo[1] = p.a_lo[0]; }
+  if ((r = wmap(h, &p.w_hi, h->tc.w_hi + w_off, BN, K, 1, 0))) return r;
+  p.w_lo = p.w_hi;
+  if (x3 && (r = wmap(h, &p.w_lo, h->tc.w_lo + w_off, BN, K, 1, 0))) return r;
+  if ((r = wmap(h, &p.w_hi_half, h->tc.w_hi + w_off, BN, K, 1, 0, BN / 2))) return r;
+  p.w_lo_half = p.w_hi_half;
+  if (x3 && (r = wmap(h, &p.w_lo_half, h->tc.w_lo + w_off, BN, K, 1, 0, BN / 2))) return r;
+  if (out_f32) {
+    if ((r = omap2d(h, &p.o_f32, out_f32, 4, ldo, rows, 32, true))) return r;
+  } else {
+    if ((r = omap2d(h, &p.o_h, out_h, 2, cout, rows, 64, true))) return r;
+    if (p.out_l && (r = omap2d(h, &p.o_l32, out_l, 2, cout, rows, 32, false))) return r;
+  }
+  p.kb0 = p.kb_total = K / BK;
+  p.passes = x3 ? 3 : 1;
+  p.st = st; p.w_select = 0; p.dbg = h->tc.dbg;
+  p.conv_cb = taps == 9 ? cin / BK : 0;
+  p.conv_w2 = W + 2; p.conv_h = H; p.conv_w = W;
+  p.conv_plane = (long)(H + 2) * (W + 2); p.conv_rows = (long)B * p.conv_plane;
+  h->launches += 1;
+  return launch_linear(p, 1, stream);
 }
 
 int tc_block(LgHandle* h, const TcBuffers& b, const SeqState& st, int layer, int blk, float* x, const float* cs,

@@ -5,10 +5,12 @@
 #include "../../include/superpoint_b200.h"
 #include "lg_internal.h"
 #include "sp_pipeline.h"
+#include "sp_tc.h"
 
 struct SpHandle {
   SpConfig cfg;
   float* wts;  // device copy of the weight blob
+  SpTc* tc;    // tensor-core backbone (cfg.precision == 1), else null
 };
 
 namespace {
@@ -48,17 +50,23 @@ extern "C" int sp_create(const SpConfig* cfg, const float* weights_dev, size_t n
   if (cfg->abi_version != SP_ABI_VERSION) return lg_set_error("sp_create: ABI version mismatch");
   if (n_floats != sp_blob_floats()) return lg_set_error("sp_create: weight blob has the wrong size");
   if (cfg->nms_radius < 0 || cfg->remove_borders < 0) return lg_set_error("sp_create: bad conf");
-  SpHandle* h = new SpHandle{*cfg, nullptr};
+  if (cfg->precision != 0 && cfg->precision != 1) return lg_set_error("sp_create: bad precision");
+  SpHandle* h = new SpHandle{*cfg, nullptr, nullptr};
   cudaError_t e = cudaMalloc(&h->wts, n_floats * sizeof(float));
   if (e != cudaSuccess) { delete h; return lg_set_cuda_error(e, __FILE__, __LINE__); }
   e = cudaMemcpyAsync(h->wts, weights_dev, n_floats * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream_);
   if (e != cudaSuccess) { cudaFree(h->wts); delete h; return lg_set_cuda_error(e, __FILE__, __LINE__); }
+  if (cfg->precision == 1) {
+    int r = sp_tc_create(&h->tc, h->wts, (cudaStream_t)stream_);
+    if (r) { cudaFree(h->wts); delete h; return r; }
+  }
   *out = h;
   return 0;
 }
 
 extern "C" int sp_destroy(SpHandle* h) {
   if (!h) return 0;
+  sp_tc_destroy(h->tc);
   cudaFree(h->wts);
   delete h;
   return 0;
@@ -70,7 +78,7 @@ extern "C" size_t sp_workspace_bytes(const SpHandle* h, int32_t B, int32_t H, in
   if (!h || B <= 0 || H <= 0 || W <= 0) return 0;
   SpWorkspace w;
   sp_carve(nullptr, B, H, W, max_keypoints(h->cfg, H, W), &w);
-  return w.bytes;
+  return w.bytes + (h->tc ? sp_tc_workspace_bytes(B, H, W) : 0);
 }
 
 extern "C" int sp_forward(SpHandle* h, const float* image, int32_t B, int32_t H, int32_t W, int64_t cap, float* keypoints,
@@ -81,11 +89,18 @@ extern "C" int sp_forward(SpHandle* h, const float* image, int32_t B, int32_t H,
   if (cap < max_keypoints(h->cfg, H, W)) return lg_set_error("sp_forward: output capacity below sp_max_keypoints()");
   SpWorkspace w;
   sp_carve((char*)workspace, B, H, W, cap, &w);
-  if (!workspace || workspace_bytes < w.bytes) return lg_set_error("sp_forward: workspace too small");
+  const size_t need = w.bytes + (h->tc ? sp_tc_workspace_bytes(B, H, W) : 0);
+  if (!workspace || workspace_bytes < need) return lg_set_error("sp_forward: workspace too small");
   cudaStream_t stream = (cudaStream_t)stream_;
   CudaExec ex{stream};
   const SpParams prm{h->cfg.nms_radius, h->cfg.max_num_keypoints, h->cfg.remove_borders, h->cfg.detection_threshold};
-  int rc = sp_run(ex, h->wts, prm, image, B, H, W, cap, w, keypoints, scores, descriptors);
+  int rc;
+  if (h->tc) {  // convolutions on the tensor cores, then the shared post-processing functors
+    rc = sp_tc_backbone(h->tc, h->wts, image, B, H, W, (char*)workspace + w.bytes, w.logits, w.dense, stream);
+    if (!rc) rc = sp_run_post(ex, prm, B, H, W, cap, w, keypoints, scores, descriptors);
+  } else {
+    rc = sp_run(ex, h->wts, prm, image, B, H, W, cap, w, keypoints, scores, descriptors);
+  }
   if (rc) return rc;
   cudaError_t e = cudaMemcpyAsync(counts, w.n_sel, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
   if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);

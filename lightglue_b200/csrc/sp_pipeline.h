@@ -311,9 +311,9 @@ inline void sp_carve(char* base, int B, int H, int W, long out_cap, SpWorkspace*
 // `exec.run(f)` executes functor f for every index in [0, f.count()); returns non-zero on failure.
 // Outputs: kpts [B,out_cap,2] (x, y), kscores [B,out_cap], desc [B,out_cap,256], counts = ws.n_sel [B].
 // ---------------------------------------------------------------------------------------------------------------
+// Part 1: the convolution stack -> ws.logits [B,65,Hc,Wc], ws.dense [B,256,Hc,Wc] (un-normalised), fp32 NCHW.
 template <class Exec>
-int sp_run(Exec& exec, const float* wts, const SpParams& prm, const float* image, int B, int H, int W, long out_cap,
-           const SpWorkspace& ws, float* kpts, float* kscores, float* desc) {
+int sp_run_backbone(Exec& exec, const float* wts, const float* image, int B, int H, int W, const SpWorkspace& ws) {
   auto conv = [&](int l, const float* in, float* out, int h, int w_, int relu) {
     const float* base = wts + sp_layer_offset(l);
     const SpLayer& L = SP_LAYERS[l];
@@ -337,10 +337,22 @@ int sp_run(Exec& exec, const float* wts, const SpParams& prm, const float* image
   h /= 2; w_ /= 2;  // = Hc, Wc
   if ((rc = conv(6, ws.bufA, ws.bufB, h, w_, 1))) return rc;
   if ((rc = conv(7, ws.bufB, ws.bufA, h, w_, 1))) return rc;  // feat = bufA [B,128,Hc,Wc]
-  const int Hc = h, Wc = w_;
-  // detector head (184-190)
-  if ((rc = conv(8, ws.bufA, ws.bufB, Hc, Wc, 1))) return rc;
-  if ((rc = conv(9, ws.bufB, ws.logits, Hc, Wc, 0))) return rc;
+  // detector head (184-185)
+  if ((rc = conv(8, ws.bufA, ws.bufB, h, w_, 1))) return rc;
+  if ((rc = conv(9, ws.bufB, ws.logits, h, w_, 0))) return rc;
+  // descriptor head (220-221)
+  if ((rc = conv(10, ws.bufA, ws.bufB, h, w_, 1))) return rc;
+  if ((rc = conv(11, ws.bufB, ws.dense, h, w_, 0))) return rc;
+  return 0;
+}
+
+// Part 2: scores, NMS, keypoint selection, descriptor normalisation + sampling on ws.logits / ws.dense.
+template <class Exec>
+int sp_run_post(Exec& exec, const SpParams& prm, int B, int H, int W, long out_cap, const SpWorkspace& ws, float* kpts,
+                float* kscores, float* desc) {
+  int rc = 0;
+  const int Hc = H / SP_CELL, Wc = W / SP_CELL;
+  // detector scores (186-190)
   { SpScores s{ws.logits, ws.scores, B, Hc, Wc}; if ((rc = exec.run(s))) return rc; }
   // simple_nms (52-68)
   const long n = (long)B * H * W;
@@ -369,10 +381,16 @@ int sp_run(Exec& exec, const float* wts, const SpParams& prm, const float* image
   { SpRowWrite s{ws.t0, ws.row_start, ws.cand_pos, ws.cand_score, B, H, W, prm.detection_threshold, cap}; if ((rc = exec.run(s))) return rc; }
   { SpSelect s{ws.n_cand, ws.cand_pos, ws.cand_score, ws.sel_pos, ws.sel_score, ws.n_sel, B, prm.max_num_keypoints, cap, out_cap};
     if ((rc = exec.run(s))) return rc; }
-  // descriptor head (220-226)
-  if ((rc = conv(10, ws.bufA, ws.bufB, Hc, Wc, 1))) return rc;
-  if ((rc = conv(11, ws.bufB, ws.dense, Hc, Wc, 0))) return rc;
+  // descriptors (222-226)
   { SpNormalizeDense s{ws.dense, B, Hc, Wc}; if ((rc = exec.run(s))) return rc; }
   { SpSample s{ws.n_sel, ws.sel_pos, ws.sel_score, ws.dense, kpts, kscores, desc, B, Hc, Wc, out_cap}; if ((rc = exec.run(s))) return rc; }
   return 0;
+}
+
+template <class Exec>
+int sp_run(Exec& exec, const float* wts, const SpParams& prm, const float* image, int B, int H, int W, long out_cap,
+           const SpWorkspace& ws, float* kpts, float* kscores, float* desc) {
+  int rc = sp_run_backbone(exec, wts, image, B, H, W, ws);
+  if (rc) return rc;
+  return sp_run_post(exec, prm, B, H, W, out_cap, ws, kpts, kscores, desc);
 }

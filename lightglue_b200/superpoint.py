@@ -35,6 +35,9 @@ class SuperPoint(nn.Module):
         "remove_borders": 4,
         # extension: None = keep the (random) initial parameters instead of looking for superpoint_v1.pth
         "weights": "superpoint_v1",
+        # extension: arithmetic of the twelve convolutions -- "bf16x3" (tcgen05 tensor cores, split-bf16 operands,
+        # fp32 accumulate) or "fp32" (CUDA cores: the checker the tensor-core path is validated against)
+        "precision": "bf16x3",
     }
     preprocess_conf = {"resize": 1024}  # superpoint.py:120-122
     required_data_keys = ["image"]
@@ -45,6 +48,8 @@ class SuperPoint(nn.Module):
         self.conf = SimpleNamespace(**{**self.default_conf, **conf})
         if self.conf.descriptor_dim != 256:
             raise ValueError("descriptor_dim is fixed to 256 by the SuperPoint weights")
+        if self.conf.precision not in ("fp32", "bf16x3"):
+            raise ValueError("precision must be 'fp32' or 'bf16x3'")
         if self.conf.max_num_keypoints is not None and self.conf.max_num_keypoints <= 0:
             raise ValueError("max_num_keypoints must be positive or None")  # superpoint.py:158-159
         for name, co, ci, k in LAYERS:  # parameter containers with the reference's names; the math runs in CUDA
@@ -81,14 +86,16 @@ class SuperPoint(nn.Module):
     def _get_handle(self, device: torch.device):
         lib = _cabi.load()
         sig = (device.index, tuple(int(getattr(self, n).weight._version) for n, *_ in LAYERS),
-               self.conf.nms_radius, self.conf.max_num_keypoints, self.conf.remove_borders, self.conf.detection_threshold)
+               self.conf.nms_radius, self.conf.max_num_keypoints, self.conf.remove_borders, self.conf.detection_threshold,
+               self.conf.precision)
         if self._handle is not None and self._handle[1] == sig:
             return self._handle[0]
         self._release()
         blob = self._blob().to(device)
         assert blob.numel() == lib.sp_weight_blob_floats()
         cfg = _cabi.SpConfig(_cabi.SP_ABI_VERSION, int(self.conf.nms_radius), int(self.conf.max_num_keypoints or 0),
-                             int(self.conf.remove_borders), float(self.conf.detection_threshold))
+                             int(self.conf.remove_borders), float(self.conf.detection_threshold),
+                             1 if self.conf.precision == "bf16x3" else 0)
         h = C.c_void_p()
         stream = torch.cuda.current_stream(device).cuda_stream
         _cabi.check(lib.sp_create(C.byref(cfg), blob.data_ptr(), blob.numel(), stream, C.byref(h)), "sp_create")
