@@ -315,6 +315,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-other-mode", action="store_true")
+    ap.add_argument("--no-extractor", action="store_true")
     ap.add_argument("--profile", action="store_true", help="2 forwards and exit (for ncu; prints nothing timed)")
     args = ap.parse_args()
 
@@ -550,6 +551,63 @@ def main():
         except Exception as exc:  # noqa: BLE001
             other_mode = {"error": repr(exc)}
 
+    # ---- next scope row: the SuperPoint extractor that produces the matcher's inputs, and extract + match
+    # of one image pair (utils.match_pair, reference utils.py:150-165).  Random-init weights (no checkpoint offline), a
+    # random 768 x 1024 image (the reference's default extraction size, resize = 1024), top-2048 keypoints.
+    extractor = None
+    if rank == 0 and not args.no_extractor:
+        try:
+            from lightglue_b200.superpoint import SuperPoint
+            from lightglue_b200.utils import match_pair
+
+            g = torch.Generator().manual_seed(11)
+            im0 = torch.rand(1, 768, 1024, generator=g).to(dev)
+            im1 = torch.roll(im0, shifts=(8, 16), dims=(1, 2))
+            flops_img = 0.0
+            hw = {0: 768 * 1024, 1: 768 * 1024, 2: 384 * 512, 3: 384 * 512, 4: 192 * 256, 5: 192 * 256}
+            layers = [(64, 1, 3), (64, 64, 3), (64, 64, 3), (64, 64, 3), (128, 64, 3), (128, 128, 3), (128, 128, 3), (128, 128, 3),
+                      (256, 128, 3), (65, 256, 1), (256, 128, 3), (256, 256, 1)]
+            for li, (co, ci, k) in enumerate(layers):
+                flops_img += 2.0 * co * ci * k * k * hw.get(li, 96 * 128)
+            res = {"image": "768x1024 grayscale, synthetic", "max_num_keypoints": 2048, "algorithmic_flops_per_image": flops_img}
+            peaks, how = measured_peaks()
+            for prec in ("bf16x3", "fp32"):
+                sp = SuperPoint(weights=None, max_num_keypoints=2048, precision=prec).eval().to(dev)
+                for _ in range(2):
+                    sp({"image": im0[None]})
+                torch.cuda.synchronize()
+                reps = 10 if prec == "bf16x3" else 3
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(reps):
+                    sp({"image": im0[None]})
+                a1.record()
+                torch.cuda.synchronize()
+                ms_img = a0.elapsed_time(a1) / reps
+                res[prec] = {"ms_per_image": ms_img, "images_per_s": 1000.0 / ms_img,
+                             "algorithmic_tflops": flops_img / (ms_img * 1e-3) / 1e12,
+                             "frac_of_bf16_peak": flops_img / (ms_img * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", 1400.0)}
+                if prec == "bf16x3":
+                    lg1 = LightGlue(features=None, depth_confidence=-1, width_confidence=-1, precision=args.precision)
+                    lg1.load_state_dict(sd, strict=False)
+                    lg1 = lg1.eval().to(dev)
+                    for _ in range(2):
+                        match_pair(sp, lg1, im0, im1, device=dev, resize=None)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(10):
+                        f0, f1, m01 = match_pair(sp, lg1, im0, im1, device=dev, resize=None)
+                    torch.cuda.synchronize()
+                    ms_pair = (time.perf_counter() - t0) / 10 * 1e3
+                    res["match_pair"] = {"ms_per_pair": ms_pair, "pairs_per_s": 1000.0 / ms_pair, "keypoints": int(f0["keypoints"].shape[0]),
+                                         "what": "extract(image0) + extract(image1) + LightGlue forward, one pair at a time, host-synchronous "
+                                                 "like the reference's utils.match_pair"}
+                    del lg1
+                del sp
+            extractor = res
+        except Exception as exc:  # noqa: BLE001
+            extractor = {"error": repr(exc)[:300]}
+
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         cpu = CpuReference()
@@ -595,6 +653,7 @@ def main():
             "roofline": roofline,
             "roofline_assign": roofline_assign,
             "other_mode": other_mode,
+            "extractor": extractor,
             "cpu_baseline": cpu_baseline,
             "reference_gpu": reference_gpu,
             "kernel_ms": kernel_ms,

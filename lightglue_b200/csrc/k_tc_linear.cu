@@ -55,6 +55,8 @@ struct TcLinParams {
   // pixels again on the way out (conv_w2 = W + 2, conv_plane = (H+2)(W+2), conv_rows = B conv_plane) and applies ReLU.
   int conv_cb, conv_w2, conv_h, conv_w, relu;
   long conv_plane, conv_rows;
+  int mma_n;  // pair mode only: N of the MMAs when fewer than 256 output columns exist (64 / 128; 0 = 256): each CTA then
+              // holds mma_n / 2 rows of the W tile and the accumulator uses the first mma_n columns of its slot
   // epilogue tensor maps (all boxes are 32 rows x 128 bytes, 128B swizzle)
   CUtensorMap o_h;          // bf16 hi output [rows, ldb], box 64 cols x 32 rows, 128B swizzle (two chunks per store)
   CUtensorMap o_l32;        // bf16 lo output, box 32 cols x 32 rows, no swizzle (one chunk per store)
@@ -272,8 +274,9 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
               kc = (kb % p.conv_cb) * BK;
               seg = 0;
             }
-            const int wrow = (ti.n_tile * NSLOT + sl_) * BN + rank * (BN / 2);
-            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+            const int wpart = p.mma_n ? p.mma_n * (BK * 2 / 2) : C::W_PART;  // bytes of this CTA's half of the W tile
+            const int wrow = (ti.n_tile * NSLOT + sl_) * BN + rank * (p.mma_n ? p.mma_n / 2 : BN / 2);
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (X3 ? 2 * A_TILE_BYTES + 2 * wpart : A_TILE_BYTES + wpart));
             if (X3) {
               tma_load_2d_cg2(sa, &p.a_hi[seg], kc, arow, &full[stage]);
               tma_load_2d_cg2(sa + A_TILE_BYTES, &p.a_lo[seg], kc, arow, &full[stage]);
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc(CG2 ? 2 * BM : BM, BN, true);
+    const uint32_t idesc = make_idesc(CG2 ? 2 * BM : BM, (CG2 && p.mma_n) ? p.mma_n : BN, true);
     int g = 0, li = 0;  // li: index among this CTA's live tiles
     TileWalk<MC> walk(total_tiles, n_tiles);
     TileInfo ti;
@@ -1216,9 +1219,11 @@ int tc_conv(LgHandle* h, const SeqState& st, const __nv_bfloat16* in_h, const __
   if ((r = wmap(h, &p.w_hi, h->tc.w_hi + w_off, BN, K, 1, 0))) return r;
   p.w_lo = p.w_hi;
   if (x3 && (r = wmap(h, &p.w_lo, h->tc.w_lo + w_off, BN, K, 1, 0))) return r;
-  if ((r = wmap(h, &p.w_hi_half, h->tc.w_hi + w_off, BN, K, 1, 0, BN / 2))) return r;
+  const int mma_n = cout <= 64 ? 64 : cout <= 128 ? 128 : BN;  // no MMA columns for the zero rows of a narrow layer
+  p.mma_n = mma_n == BN ? 0 : mma_n;
+  if ((r = wmap(h, &p.w_hi_half, h->tc.w_hi + w_off, BN, K, 1, 0, mma_n / 2))) return r;
   p.w_lo_half = p.w_hi_half;
-  if (x3 && (r = wmap(h, &p.w_lo_half, h->tc.w_lo + w_off, BN, K, 1, 0, BN / 2))) return r;
+  if (x3 && (r = wmap(h, &p.w_lo_half, h->tc.w_lo + w_off, BN, K, 1, 0, mma_n / 2))) return r;
   if (out_f32) {
     if ((r = omap2d(h, &p.o_f32, out_f32, 4, ldo, rows, 32, true))) return r;
   } else {

@@ -104,12 +104,12 @@ class SuperPoint(nn.Module):
         return h
 
     def _release(self):
-        if getattr(self, "_handle", None) is not None:  # (the constructor may have raised before the attribute exists)
-            try:
+        try:
+            if getattr(self, "_handle", None) is not None:  # (the constructor may have raised before the attribute exists)
                 _cabi.load().sp_destroy(self._handle[0])
-            except Exception:  # noqa: BLE001  (interpreter shutdown)
-                pass
-            self._handle = None
+                object.__setattr__(self, "_handle", None)
+        except Exception:  # noqa: BLE001  (interpreter shutdown: modules may already be torn down)
+            pass
 
     def __del__(self):
         self._release()
