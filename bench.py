@@ -67,9 +67,9 @@ def profiled_traffic(kernel: str, batch: int, precision: str):
         return None
     with open(path) as f:
         d = json.load(f)
-    if d.get("workload") != f"superpoint_n{N_KPTS}_l9_prune_off_b{batch}" or d.get("precision") != precision:
+    if d.get("workload") != f"superpoint_n{N_KPTS}_l9_prune_off_b{batch}":
         return None
-    return d.get(kernel, {}).get("bytes_per_launch")
+    return ((d.get(precision) or {}).get(kernel) or {}).get("bytes_per_launch")
 
 
 class ClockSampler:

@@ -18,9 +18,10 @@ ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--n", type=int, default=2048)
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--time", action="store_true")
+ap.add_argument("--precision", default="bf16x3")
 a = ap.parse_args()
 
-m = LightGlue(features=None, precision="bf16", depth_confidence=-1, width_confidence=-1)
+m = LightGlue(features=None, precision=a.precision, depth_confidence=-1, width_confidence=-1)
 m.load_state_dict(synth.make_state_dict(), strict=False)
 m = m.eval().cuda()
 g = torch.Generator(device="cuda").manual_seed(0)
