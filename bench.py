@@ -7,7 +7,7 @@
 Workload at N GPUs: BASELINE.json configs[1] on every GPU -- SuperPoint-shaped synthetic pairs,
 2048 keypoints, d=256, 9 layers, pruning / early exit OFF, batch = 32 pairs per step per GPU (weak
 scaling: pairs are independent, each rank matches its own shard; the only collective is the final
-all_gather of the match indices).  One "step" = one forward over one batch.
+all_gather of the match indices and scores).  One "step" = one forward over one batch.
 
 Prints ONE JSON line (rank 0).  `value` = pairs/s with inputs resident in HBM; `e2e` = pairs/s
 through the public `LightGlue.forward` API with pinned HOST inputs (H2D and the D2H of the results
@@ -371,35 +371,32 @@ def main():
         """n_steps forwards on resident inputs.  in_flight = 1: step i+1 is enqueued before step i's host-side result
         (stop, per-pair match lists) is resolved, so the GPU never waits for the host; in_flight = 0: every forward is
         resolved before the next is enqueued (the reference's calling pattern).  Either way every step's result is
-        resolved before the function returns.  N > 1: each step also gathers the match indices (int32 on the wire)."""
+        resolved before the function returns.  N > 1: the results of all steps are gathered once, after the last forward."""
         prev, last = None, None
-        works, keep = [], []
+        acc_i, acc_s = [], []
         for _ in range(n_steps):
             cur = matcher.forward_async(resident)
             if world > 1:
                 # SURVEY 8e: the fixed-size results of every rank -- match indices of both images as int32 on the wire,
-                # both score tensors -- are gathered (2 collectives, 2 MB per rank); asynchronous, so the next
-                # forward's kernels are not serialised behind the collective
+                # both score tensors -- are collected on the device and gathered ONCE for the run, after the last forward
+                # (still inside the timed region).  A collective per step, concurrent with the next forward, cost 16 % at
+                # two ranks: its channels hold SMs while they wait for the slower rank, and the persistent CTA-pair
+                # kernels then run short of SMs.
                 tt = cur.tensors
-                wi = torch.cat([tt["matches0"], tt["matches1"]], 1).to(torch.int32)
-                ws = torch.cat([tt["matching_scores0"], tt["matching_scores1"]], 1)
-                gi = torch.empty(world, *wi.shape, dtype=wi.dtype, device=dev)
-                gs = torch.empty(world, *ws.shape, dtype=ws.dtype, device=dev)
-                works.append(dist.all_gather_into_tensor(gi, wi, async_op=True))
-                works.append(dist.all_gather_into_tensor(gs, ws, async_op=True))
-                keep.append((gi, gs, wi, ws))
-                while len(works) > 4:
-                    works.pop(0).wait()
-                    if len(keep) > 3:
-                        keep.pop(0)
+                acc_i.append(torch.cat([tt["matches0"], tt["matches1"]], 1).to(torch.int32))
+                acc_s.append(torch.cat([tt["matching_scores0"], tt["matching_scores1"]], 1))
             if in_flight == 0:
                 last = cur.result()
                 continue
             if prev is not None:
                 last = prev.result()
             prev = cur
-        for w in works:
-            w.wait()
+        if world > 1:
+            wi, ws = torch.stack(acc_i), torch.stack(acc_s)  # [steps, B, M + N]
+            gi = torch.empty(world, *wi.shape, dtype=wi.dtype, device=dev)
+            gs = torch.empty(world, *ws.shape, dtype=ws.dtype, device=dev)
+            dist.all_gather_into_tensor(gi, wi)
+            dist.all_gather_into_tensor(gs, ws)
         return prev.result() if prev is not None else last
 
     # warm-up: W steps in each host calling pattern (also absorbs their one-time allocations), timed to pick the
