@@ -97,7 +97,7 @@ extern "C" int sp_forward(SpHandle* h, const float* image, int32_t B, int32_t H,
   int rc;
   if (h->tc) {  // convolutions on the tensor cores, then the shared post-processing functors
     rc = sp_tc_backbone(h->tc, h->wts, image, B, H, W, (char*)workspace + w.bytes, w.logits, w.dense, stream);
-    if (!rc) rc = sp_run_post(ex, prm, B, H, W, cap, w, keypoints, scores, descriptors);
+    if (!rc) rc = sp_run_post(ex, prm, B, H, W, cap, w, keypoints, scores, descriptors, SpCudaStages{stream});
   } else {
     rc = sp_run(ex, h->wts, prm, image, B, H, W, cap, w, keypoints, scores, descriptors);
   }

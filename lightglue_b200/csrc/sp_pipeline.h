@@ -346,10 +346,36 @@ int sp_run_backbone(Exec& exec, const float* wts, const float* image, int B, int
   return 0;
 }
 
+// The three heavy post-processing stages as one-logical-thread functors (the semantic definition, also run on the host by
+// oracle/sp_emul.cpp).  The CUDA build substitutes warp / block kernels with the same results (sp_tc.cu SpCudaStages).
+struct SpFunctorStages {
+  // candidates = where(scores > threshold), row-major per image (201-208)
+  template <class Exec>
+  int compact(Exec& exec, const SpWorkspace& ws, int B, int H, int W, float thr, long cap) const {
+    int rc;
+    { SpRowCount s{ws.t0, ws.row_count, B, H, W, thr}; if ((rc = exec.run(s))) return rc; }
+    { SpRowScan s{ws.row_count, ws.row_start, ws.n_cand, B, H}; if ((rc = exec.run(s))) return rc; }
+    { SpRowWrite s{ws.t0, ws.row_start, ws.cand_pos, ws.cand_score, B, H, W, thr, cap}; if ((rc = exec.run(s))) return rc; }
+    return 0;
+  }
+  // top-k by score, descending, ties by candidate index (71-76, 210-218)
+  template <class Exec>
+  int select(Exec& exec, const SpWorkspace& ws, int B, int k, long cap, long out_cap) const {
+    SpSelect s{ws.n_cand, ws.cand_pos, ws.cand_score, ws.sel_pos, ws.sel_score, ws.n_sel, B, k, cap, out_cap};
+    return exec.run(s);
+  }
+  // keypoints, scores, bilinearly sampled + normalised descriptors (79-96, 217-226)
+  template <class Exec>
+  int sample(Exec& exec, const SpWorkspace& ws, float* kpts, float* kscores, float* desc, int B, int Hc, int Wc, long out_cap) const {
+    SpSample s{ws.n_sel, ws.sel_pos, ws.sel_score, ws.dense, kpts, kscores, desc, B, Hc, Wc, out_cap};
+    return exec.run(s);
+  }
+};
+
 // Part 2: scores, NMS, keypoint selection, descriptor normalisation + sampling on ws.logits / ws.dense.
-template <class Exec>
+template <class Exec, class Stages = SpFunctorStages>
 int sp_run_post(Exec& exec, const SpParams& prm, int B, int H, int W, long out_cap, const SpWorkspace& ws, float* kpts,
-                float* kscores, float* desc) {
+                float* kscores, float* desc, const Stages& stages = Stages()) {
   int rc = 0;
   const int Hc = H / SP_CELL, Wc = W / SP_CELL;
   // detector scores (186-190)
@@ -376,14 +402,11 @@ int sp_run_post(Exec& exec, const SpParams& prm, int B, int H, int W, long out_c
   if (prm.remove_borders > 0) { SpBorders s{ws.t0, B, H, W, prm.remove_borders}; if ((rc = exec.run(s))) return rc; }
   // keypoints (201-218)
   const long cap = (long)H * W;
-  { SpRowCount s{ws.t0, ws.row_count, B, H, W, prm.detection_threshold}; if ((rc = exec.run(s))) return rc; }
-  { SpRowScan s{ws.row_count, ws.row_start, ws.n_cand, B, H}; if ((rc = exec.run(s))) return rc; }
-  { SpRowWrite s{ws.t0, ws.row_start, ws.cand_pos, ws.cand_score, B, H, W, prm.detection_threshold, cap}; if ((rc = exec.run(s))) return rc; }
-  { SpSelect s{ws.n_cand, ws.cand_pos, ws.cand_score, ws.sel_pos, ws.sel_score, ws.n_sel, B, prm.max_num_keypoints, cap, out_cap};
-    if ((rc = exec.run(s))) return rc; }
+  if ((rc = stages.compact(exec, ws, B, H, W, prm.detection_threshold, cap))) return rc;
+  if ((rc = stages.select(exec, ws, B, prm.max_num_keypoints, cap, out_cap))) return rc;
   // descriptors (222-226)
   { SpNormalizeDense s{ws.dense, B, Hc, Wc}; if ((rc = exec.run(s))) return rc; }
-  { SpSample s{ws.n_sel, ws.sel_pos, ws.sel_score, ws.dense, kpts, kscores, desc, B, Hc, Wc, out_cap}; if ((rc = exec.run(s))) return rc; }
+  if ((rc = stages.sample(exec, ws, kpts, kscores, desc, B, Hc, Wc, out_cap))) return rc;
   return 0;
 }
 
