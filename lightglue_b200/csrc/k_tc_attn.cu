@@ -34,6 +34,7 @@ struct AttnParams {
   __nv_bfloat16* ctxh; __nv_bfloat16* ctxl;
   int kv_shift;
   int rows_per_cta;  // 256 (two query tiles per CTA) or 128 (one: small problems that would not fill the SMs)
+  float rescale_log2;  // lazy rescaling: O / l are rescaled only when the row maximum grows by more than 2^rescale_log2
   int pingpong;      // alternate the exponential phases of the CTA's two query tiles (LG_ATTN_NO_PINGPONG=1 switches it off)
   SeqState st;
   unsigned int* dbg;
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
           bool need = false;
           if (mx > m_used) {
             if (m_used == -INFINITY) { m_used = mx; }
-            else if ((mx - m_used) * SCALE_LOG2 > 8.f) { alpha = ex2((m_used - mx) * SCALE_LOG2); m_used = mx; need = true; }
+            else if ((mx - m_used) * SCALE_LOG2 > p.rescale_log2) { alpha = ex2((m_used - mx) * SCALE_LOG2); m_used = mx; need = true; }
           }
           if (__any_sync(0xffffffffu, need)) {  // S_t(j) was issued after P_t(j-1) V: that MMA has retired
 #pragma unroll 1
@@ -366,6 +367,9 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
   p.ctxh = b.ctxh; p.ctxl = b.ctxl; p.kv_shift = kv_shift; p.st = st; p.dbg = h->tc.dbg;
   dim3 grid((st.Lp + 2 * QT - 1) / (2 * QT), LG_HEADS, st.S);
   p.rows_per_cta = 2 * QT;
+  // P = 2^x with x <= rescale_log2 stays far inside fp16 (65504 = 2^16) and the fp32 accumulators
+  static const float rescale = getenv("LG_ATTN_RESCALE_LOG2") ? (float)atof(getenv("LG_ATTN_RESCALE_LOG2")) : 8.f;
+  p.rescale_log2 = rescale;
   static const bool no_pp = getenv("LG_ATTN_NO_PINGPONG") && atoi(getenv("LG_ATTN_NO_PINGPONG")) != 0;
   p.pingpong = no_pp ? 0 : 1;
   if ((long)grid.x * grid.y * grid.z < 2 * lg_num_sms()) {  // fewer CTAs than resident slots: one query tile per CTA instead
