@@ -501,7 +501,7 @@ def main():
             abytes = 18.9e6 * B
             ach = abytes / ((st_ms / st_n) / 1000.0) / 1e9
             roofline_assign = {"kernel": "materialising assignment STAGE: final_proj + LSE sweep + arg-max sweep with the "
-                                         "[B, M+1, N+1] fp32 matrix write + combines + dustbin + filter + output",
+                                         "[B, M+1, N+1] fp32 matrix write + term + dustbin + tail (filter, outputs)",
                                "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                "frac": ach / peaks["hbm_gbs"],
                                "traffic": profiled_traffic("assign_matrix", B, args.precision),

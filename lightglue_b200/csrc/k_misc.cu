@@ -531,10 +531,8 @@ __global__ void assign_combine_kernel(AssignArgs a, SeqState st, int mode) {
   }
 }
 
-// filter_matches (302-318) in the compact index space
-__global__ void assign_filter_kernel(AssignArgs a, SeqState st) {
-  const int b = blockIdx.y;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// filter_matches (302-318) in the compact index space: row/column `idx` of pair b
+__device__ __forceinline__ void assign_filter_one(const AssignArgs& a, const SeqState& st, int b, int idx) {
   const int m = st.len[b], n = st.len[b + st.B];
   const long rbase = (long)b * st.Lp;
   if (m == 0 || n == 0) {  // an empty image: nothing to match against (568-588); the arg-max slots hold no data
@@ -561,6 +559,9 @@ __global__ void assign_filter_kernel(AssignArgs a, SeqState st) {
     a.m1c[rbase + idx] = (mutual1 && valid0_i) ? i : -1;
   }
 }
+__global__ void assign_filter_kernel(AssignArgs a, SeqState st) {
+  assign_filter_one(a, st, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+}
 
 // dustbin row / column and corner of the materialised matrix (275-276)
 __global__ void assign_dustbin_kernel(AssignArgs a, SeqState st) {
@@ -572,21 +573,12 @@ __global__ void assign_dustbin_kernel(AssignArgs a, SeqState st) {
   if (idx == 0) o[(long)a.M * (a.N + 1) + a.N] = 0.f;
 }
 
-// scatter back to the original indexing (605-614) + the compact `matches` / `scores` lists (593-602)
-__global__ void __launch_bounds__(1024) assign_output_kernel(AssignArgs a, SeqState st) {
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int m = st.len[b], n = st.len[b + st.B];
+// the compact `matches` / `scores` lists (593-602): ordered compaction of the valid rows of pair b by one 1024-thread block
+__device__ __forceinline__ void assign_compact_pair(const AssignArgs& a, const SeqState& st, int b, int tid) {
+  const int m = st.len[b];
   const long rbase = (long)b * st.Lp;
   const int* ind0 = a.ind + rbase;
   const int* ind1 = a.ind + (long)(b + st.B) * st.Lp;
-  for (int i = tid; i < a.M; i += 1024) { a.matches0[(long)b * a.M + i] = -1; a.mscores0[(long)b * a.M + i] = 0.f; }
-  for (int j = tid; j < a.N; j += 1024) { a.matches1[(long)b * a.N + j] = -1; a.mscores1[(long)b * a.N + j] = 0.f; }
-  __syncthreads();
-  for (int j = tid; j < n; j += 1024) {
-    const int i = a.m1c[rbase + j];
-    a.matches1[(long)b * a.N + ind1[j]] = i < 0 ? -1 : ind0[i];
-    a.mscores1[(long)b * a.N + ind1[j]] = a.ms1c[rbase + j];
-  }
   __shared__ int warp_sums[32];
   __shared__ int carry;
   if (tid == 0) carry = 0;
@@ -594,11 +586,7 @@ __global__ void __launch_bounds__(1024) assign_output_kernel(AssignArgs a, SeqSt
   for (int base = 0; base < m; base += 1024) {
     const int i = base + tid;
     int j = -1; float sc = 0.f;
-    if (i < m) {
-      j = a.m0c[rbase + i]; sc = a.ms0c[rbase + i];
-      a.matches0[(long)b * a.M + ind0[i]] = j < 0 ? -1 : ind1[j];
-      a.mscores0[(long)b * a.M + ind0[i]] = sc;
-    }
+    if (i < m) { j = a.m0c[rbase + i]; sc = a.ms0c[rbase + i]; }
     const int flag = j >= 0;
     int incl = flag;
 #pragma unroll
@@ -634,6 +622,114 @@ __global__ void __launch_bounds__(1024) assign_output_kernel(AssignArgs a, SeqSt
   if (tid == 0) a.n_matches[b] = carry;
 }
 
+// scatter back to the original indexing (605-614) + the compact lists
+__global__ void __launch_bounds__(1024) assign_output_kernel(AssignArgs a, SeqState st) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int m = st.len[b], n = st.len[b + st.B];
+  const long rbase = (long)b * st.Lp;
+  const int* ind0 = a.ind + rbase;
+  const int* ind1 = a.ind + (long)(b + st.B) * st.Lp;
+  for (int i = tid; i < a.M; i += 1024) { a.matches0[(long)b * a.M + i] = -1; a.mscores0[(long)b * a.M + i] = 0.f; }
+  for (int j = tid; j < a.N; j += 1024) { a.matches1[(long)b * a.N + j] = -1; a.mscores1[(long)b * a.N + j] = 0.f; }
+  __syncthreads();
+  for (int j = tid; j < n; j += 1024) {
+    const int i = a.m1c[rbase + j];
+    a.matches1[(long)b * a.N + ind1[j]] = i < 0 ? -1 : ind0[i];
+    a.mscores1[(long)b * a.N + ind1[j]] = a.ms1c[rbase + j];
+  }
+  for (int i = tid; i < m; i += 1024) {
+    const int j = a.m0c[rbase + i];
+    a.matches0[(long)b * a.M + ind0[i]] = j < 0 ? -1 : ind1[j];
+    a.mscores0[(long)b * a.M + ind0[i]] = a.ms0c[rbase + i];
+  }
+  assign_compact_pair(a, st, b, tid);
+}
+
+// ---- the tensor-core sweeps' companions: two launches instead of five --------------------------------------------
+// After sweep 1: matchability logit z (281-285) and term = logsigmoid(z) - LSE (270-274), one warp per row; the LSE comes
+// from the per-slot (max, sum-exp) partials the sweep wrote (`slot_cols` columns of the partner image per slot).
+__global__ void __launch_bounds__(256) assign_term_kernel(AssignArgs a, SeqState st, const float2* __restrict__ part,
+                                                          int pstride, int slot_cols, float* __restrict__ term) {
+  const int s = blockIdx.y;
+  const int r = blockIdx.x * 8 + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (r >= st.len[s]) return;
+  const int pair = s >= st.B ? s - st.B : s;
+  const int partner = s >= st.B ? s - st.B : s + st.B;
+  const long sel = a.mat_sel_stride > 0 ? (long)(st.stop_layer[pair] - 1) : 0;
+  const long row = (long)s * st.Lp + r;
+  const float z = warp_dot256(a.x + row * LG_DIM, a.mat_w + sel * a.mat_sel_stride, lane) + (a.mat_b + sel * a.mat_sel_stride)[0];
+  const int nt = (st.len[partner] + slot_cols - 1) / slot_cols;
+  const float2* pt = part + row * pstride;
+  float mx = -INFINITY;
+  for (int t = lane; t < nt; t += 32) mx = fmaxf(mx, pt[t].x);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  float se = 0.f;
+  for (int t = lane; t < nt; t += 32) se += pt[t].y * expf(pt[t].x - mx);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) se += __shfl_xor_sync(0xffffffffu, se, off);
+  if (lane == 0) {
+    a.z[row] = z;
+    term[row] = logsigmoidf_(z) - (mx + logf(se));
+  }
+}
+
+// After sweep 2: everything from the per-slot (best, arg) partials to the outputs, one cluster of 8 CTAs per pair.
+//   phase A (all CTAs)  reduce the slots of every row / column; pre-fill the outputs with "unmatched"
+//   phase B (all CTAs)  mutual-nearest filter + scatter to the original indexing
+//   phase C (CTA 0)     ordered compaction into the `matches` / `scores` lists
+// cluster barriers (release/acquire at cluster scope) order the global-memory hand-offs between the phases.
+constexpr int TAIL_CLUSTER = 8;
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__global__ void __cluster_dims__(TAIL_CLUSTER, 1, 1) __launch_bounds__(1024)
+assign_tail_kernel(AssignArgs a, SeqState st, const float* __restrict__ part, const int* __restrict__ part_arg, int pstride,
+                   int slot_cols) {
+  const int b = blockIdx.x / TAIL_CLUSTER, rank = blockIdx.x % TAIL_CLUSTER, tid = threadIdx.x;
+  const int gtid = rank * 1024 + tid, gsz = TAIL_CLUSTER * 1024;
+  const int m = st.len[b], n = st.len[b + st.B];
+  const long rbase = (long)b * st.Lp;
+  const int* ind0 = a.ind + rbase;
+  const int* ind1 = a.ind + (long)(b + st.B) * st.Lp;
+  if (m > 0 && n > 0) {
+    for (int side = 0; side < 2; ++side) {
+      const int s = b + side * st.B, len = side ? n : m;
+      const int nt = ((side ? m : n) + slot_cols - 1) / slot_cols;
+      float* obest = side ? a.colbest : a.rowbest;
+      int* oarg = side ? a.colarg : a.rowarg;
+      for (int r = gtid; r < len; r += gsz) {
+        const long base = ((long)s * st.Lp + r) * pstride;
+        float best = -INFINITY; int arg = 0;
+        for (int t = 0; t < nt; ++t)
+          if (part[base + t] > best) { best = part[base + t]; arg = part_arg[base + t]; }
+        obest[(rbase + r) * a.nt] = best; oarg[(rbase + r) * a.nt] = arg;
+      }
+    }
+  }
+  for (int i = gtid; i < a.M; i += gsz) { a.matches0[(long)b * a.M + i] = -1; a.mscores0[(long)b * a.M + i] = 0.f; }
+  for (int j = gtid; j < a.N; j += gsz) { a.matches1[(long)b * a.N + j] = -1; a.mscores1[(long)b * a.N + j] = 0.f; }
+  cluster_sync_all();
+  const int mx = m > n ? m : n;
+  for (int idx = gtid; idx < mx; idx += gsz) {
+    assign_filter_one(a, st, b, idx);
+    if (idx < m) {
+      const int j = a.m0c[rbase + idx];
+      a.matches0[(long)b * a.M + ind0[idx]] = j < 0 ? -1 : ind1[j];
+      a.mscores0[(long)b * a.M + ind0[idx]] = a.ms0c[rbase + idx];
+    }
+    if (idx < n) {
+      const int i = a.m1c[rbase + idx];
+      a.matches1[(long)b * a.N + ind1[idx]] = i < 0 ? -1 : ind0[i];
+      a.mscores1[(long)b * a.N + ind1[idx]] = a.ms1c[rbase + idx];
+    }
+  }
+  cluster_sync_all();
+  if (rank == 0) assign_compact_pair(a, st, b, tid);
+}
+
 int misc_assign_dustbin(const AssignArgs& a, const SeqState& st, cudaStream_t stream) {
   const int mx = a.M > a.N ? a.M : a.N;
   assign_dustbin_kernel<<<dim3((mx + 256) / 256, st.B), 256, 0, stream>>>(a, st);
@@ -641,20 +737,17 @@ int misc_assign_dustbin(const AssignArgs& a, const SeqState& st, cudaStream_t st
   return 0;
 }
 
-int misc_assign_z(const AssignArgs& a, const SeqState& st, cudaStream_t stream) {
-  assign_z_kernel<<<dim3(st.Lp / 8, st.S), 256, 0, stream>>>(a, st);
+int misc_assign_term(const AssignArgs& a, const SeqState& st, const float* part, int pstride, int slot_cols, float* term,
+                     cudaStream_t stream) {
+  assign_term_kernel<<<dim3(st.Lp / 8, st.S), 256, 0, stream>>>(a, st, reinterpret_cast<const float2*>(part), pstride, slot_cols, term);
   LG_CHECK_LAUNCH();
   return 0;
 }
 
-// mutual-nearest filter + output assembly on row/column arg-max results already in slot 0 of
-// rowbest/rowarg/colbest/colarg (used after the tensor-core sweeps)
-int misc_assign_tail(const AssignArgs& a, const SeqState& st, cudaStream_t stream, int64_t* launches) {
-  assign_filter_kernel<<<dim3((st.Lp + 255) / 256, st.B), 256, 0, stream>>>(a, st);
+int misc_assign_tail(const AssignArgs& a, const SeqState& st, const float* part, const int* part_arg, int pstride, int slot_cols,
+                     cudaStream_t stream) {
+  assign_tail_kernel<<<st.B * TAIL_CLUSTER, 1024, 0, stream>>>(a, st, part, part_arg, pstride, slot_cols);
   LG_CHECK_LAUNCH();
-  assign_output_kernel<<<st.B, 1024, 0, stream>>>(a, st);
-  LG_CHECK_LAUNCH();
-  *launches += 2;
   return 0;
 }
 

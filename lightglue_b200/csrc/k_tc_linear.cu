@@ -1034,43 +1034,11 @@ int run_linear(LgHandle* h, const SeqState& st, const LinDesc& d, TcLinParams& p
 // ------------------------------------------------------------------------------------------------
 // Assignment tail on the tensor cores (matches-only variant: the log-assignment matrix is never written)
 // ------------------------------------------------------------------------------------------------
-namespace {
-// partial (max, sumexp) per 256-column tile -> term[s][r] = logsigmoid(z) - LSE  (lightglue.py:270-274)
-__global__ void assign_lse_combine_kernel(const float* __restrict__ part, const float* __restrict__ z, float* __restrict__ term,
-                                          int ntc, SeqState st) {
-  const int s = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= st.len[s]) return;
-  const int partner = s >= st.B ? s - st.B : s + st.B;
-  const int nt = (st.len[partner] + BN / 2 - 1) / (BN / 2);  // 128-column slots (two per tile)
-  const float2* pt = reinterpret_cast<const float2*>(part) + ((long)s * st.Lp + r) * ntc;
-  float m = -INFINITY;
-  for (int t = 0; t < nt; ++t) m = fmaxf(m, pt[t].x);
-  float se = 0.f;
-  for (int t = 0; t < nt; ++t) se += pt[t].y * expf(pt[t].x - m);
-  const float zz = z[(long)s * st.Lp + r];
-  term[(long)s * st.Lp + r] = fminf(zz, 0.f) - log1pf(expf(-fabsf(zz))) - (m + logf(se));
-}
-// per-tile (best, arg) -> slot 0 of the [B, Lp, nt64] arrays the mutual-nearest filter reads
-__global__ void assign_best_combine_kernel(const float* __restrict__ part, const int* __restrict__ part_arg, int ntc,
-                                           float* rowbest, int* rowarg, float* colbest, int* colarg, int nt64, SeqState st) {
-  const int s = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= st.len[s]) return;
-  const int partner = s >= st.B ? s - st.B : s + st.B;
-  const int nt = (st.len[partner] + BN / 2 - 1) / (BN / 2);
-  const long base = ((long)s * st.Lp + r) * ntc;
-  float best = -INFINITY; int arg = 0;
-  for (int t = 0; t < nt; ++t)
-    if (part[base + t] > best) { best = part[base + t]; arg = part_arg[base + t]; }
-  const int b = s >= st.B ? s - st.B : s;
-  const long o = ((long)b * st.Lp + r) * nt64;
-  if (s < st.B) { rowbest[o] = best; rowarg[o] = arg; }
-  else { colbest[o] = best; colarg[o] = arg; }
-}
-}  // namespace
-
-int tc_assign_sweeps(LgHandle* h, const TcBuffers& b, const SeqState& st, const float* z, float* part, int* part_arg,
-                     float* term, float* rowbest, int* rowarg, float* colbest, int* colarg, int nt64, float* logmat, int M, int N,
-                     cudaStream_t stream) {
+// launches: sweep 1 (LSE partials), z + term, sweep 2 (arg-max partials, optionally the matrix), [dustbin], tail
+int tc_assign_sweeps(LgHandle* h, const TcBuffers& b, const SeqState& st, const AssignArgs& a, float* part, int* part_arg,
+                     float* term, cudaStream_t stream) {
+  float* logmat = a.log_assignment;
+  const int M = a.M, N = a.N;
   const int ntc = (st.Lp + BN - 1) / BN;
   for (int sweep = 0; sweep < 2; ++sweep) {
     TcLinParams p{};
@@ -1099,16 +1067,14 @@ int tc_assign_sweeps(LgHandle* h, const TcBuffers& b, const SeqState& st, const 
       if ((r = launch_linear(p, ntc, stream))) return r;
     }
     if (sweep == 0) {
-      assign_lse_combine_kernel<<<dim3((st.Lp + 255) / 256, st.S), 256, 0, stream>>>(part, z, term, 2 * ntc, st);
-      LG_CHECK_LAUNCH();
+      if ((r = misc_assign_term(a, st, part, 2 * ntc, BN / 2, term, stream))) return r;
       h->launches += 1;
     }
   }
-  assign_best_combine_kernel<<<dim3((st.Lp + 255) / 256, st.S), 256, 0, stream>>>(part, part_arg, 2 * ntc, rowbest, rowarg, colbest,
-                                                                                    colarg, nt64, st);
-  LG_CHECK_LAUNCH();
+  if (logmat) { if (int rd = misc_assign_dustbin(a, st, stream)) return rd; h->launches += 1; }
+  int r = misc_assign_tail(a, st, part, part_arg, 2 * ntc, BN / 2, stream);
   h->launches += 1;
-  return 0;
+  return r;
 }
 
 unsigned int tc_debug_timeout_code(LgHandle* h, unsigned int* words32) {

@@ -422,12 +422,7 @@ static int run_assign(LgHandle* h, const Workspace& w, const SeqState& st, const
     Timer t(h, out->log_assignment ? LG_K_OTHER : LG_K_ASSIGN, stream);
     if (h->cfg.precision != LG_PREC_FP32 && st.Lp >= 256) {
       // both similarity sweeps on the tensor cores; the N x M matrix reaches HBM only if the caller asked for it
-      RC(misc_assign_z(a, st, stream));
-      h->launches += 1;
-      RC(tc_assign_sweeps(h, w.tc, st, w.z, w.tc_part, w.tc_parg, w.term, w.rowbest, w.rowarg, w.colbest, w.colarg, w.nt,
-                          out->log_assignment, M, N, stream));
-      if (out->log_assignment) { RC(misc_assign_dustbin(a, st, stream)); h->launches += 1; }
-      RC(misc_assign_tail(a, st, stream, &h->launches));
+      RC(tc_assign_sweeps(h, w.tc, st, a, w.tc_part, w.tc_parg, w.term, stream));
     } else {
       RC(misc_assign(a, st, stream, &h->launches));
     }

@@ -147,9 +147,12 @@ struct AssignArgs {
   float* log_assignment; // optional [B, M+1, N+1]
 };
 int misc_assign(const AssignArgs& a, const SeqState& st, cudaStream_t stream, int64_t* launches);
-int misc_assign_z(const AssignArgs& a, const SeqState& st, cudaStream_t stream);
+// companions of the tensor-core sweeps: z + LSE combine (after sweep 1), slot reduce + filter + outputs (after sweep 2)
+int misc_assign_term(const AssignArgs& a, const SeqState& st, const float* part, int pstride, int slot_cols, float* term,
+                     cudaStream_t stream);
 int misc_assign_dustbin(const AssignArgs& a, const SeqState& st, cudaStream_t stream);
-int misc_assign_tail(const AssignArgs& a, const SeqState& st, cudaStream_t stream, int64_t* launches);
+int misc_assign_tail(const AssignArgs& a, const SeqState& st, const float* part, const int* part_arg, int pstride, int slot_cols,
+                     cudaStream_t stream);
 int misc_export_stop_prune(const int* stop_layer, const int* prune, int* stop_out, int* prune0, int* prune1, int B, int M,
                            int N, int Lp, cudaStream_t stream);
 

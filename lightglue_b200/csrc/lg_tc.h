@@ -37,9 +37,8 @@ int tc_block(LgHandle* h, const TcBuffers& b, const SeqState& st, int layer, int
 int tc_final_proj(LgHandle* h, const TcBuffers& b, const SeqState& st, float* p_out, cudaStream_t stream);
 // Similarity sweeps of the assignment on the tensor cores: S = p p_partner^T in both directions, row LSE
 // (sweep 1) and row arg-max of the score (sweep 2); p (bf16 hi/lo) is read from b.msgh / b.msgl.
-int tc_assign_sweeps(LgHandle* h, const TcBuffers& b, const SeqState& st, const float* z, float* part, int* part_arg,
-                     float* term, float* rowbest, int* rowarg, float* colbest, int* colarg, int nt64, float* logmat, int M, int N,
-                     cudaStream_t stream);
+int tc_assign_sweeps(LgHandle* h, const TcBuffers& b, const SeqState& st, const AssignArgs& a, float* part, int* part_arg,
+                     float* term, cudaStream_t stream);
 // softmax(q k^T / 8) v per (sequence, head): q from b.q, keys from kbuf, values from b.vt; key/value
 // sequence = (s + kv_shift) % S; writes b.ctxh (/ b.ctxl)
 int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shift, const __half* kbuf, cudaStream_t stream);
