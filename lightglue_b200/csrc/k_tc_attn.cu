@@ -269,7 +269,12 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
           // a scheduler is shared by four tiles), P store + arrive 190.  Tried and measured slower: 32-key blocks
           // with double-buffered S (473 us: the per-block fixed costs double); exponentials started speculatively
           // against the previous reference maximum with the row maximum taken in the same loop (7.70 vs 7.50 ms of
-          // attention per step: redone blocks and the longer loop body cost more than the shorter chain saves).
+          // attention per step: redone blocks and the longer loop body cost more than the shorter chain saves); P handed
+          // to the tensor pipe through shared memory (128B-swizzled A tile, fence.proxy.async) so that S_t is free once
+          // it is in registers and Q K_{j+1}^T overlaps block j's exponentials (8.47 vs 7.51 ms: the chain no longer
+          // waits for S, but every P V then reads its 16 KB A operand from shared memory on top of the 16 KB Q tile each
+          // Q K^T re-reads, 64 KB per tile and block against the SM's 128 B/clk, and the P stores cost more than
+          // tcgen05.st).
           if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(2 + t) : "memory");
           // P = exp2(c s - c m): the scale-and-shift and the row sum run as packed f32x2 operations
           const uint64_t sc2 = pack2(SCALE_LOG2, SCALE_LOG2);
