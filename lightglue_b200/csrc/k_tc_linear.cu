@@ -13,6 +13,7 @@
 //   bias + residual for ffn.3, bias * scale for input_proj / final_proj.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue
 // (warp w reads TMEM lanes 32*(w%4) .. +31, one accumulator row per thread).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <unordered_map>
@@ -94,7 +95,9 @@ struct LinCfg {
   // instruction-heaviest epilogue) runs 16 so that four warps per scheduler hide its latencies
   static constexpr int EW = NSLOT == 1 ? 8 : 16;
   static constexpr int GROUPS = EW / 4;
-  static constexpr int THREADS = 64 + EW * 32;
+  // control warps ahead of the epilogue warps: TMA producer, MMA issuer
+  static constexpr int CTRL = 2;
+  static constexpr int THREADS = (CTRL + EW) * 32;
   static constexpr int W_PART = CG2 ? W_TILE_BYTES / 2 : W_TILE_BYTES;  // bytes of one W tile held by this CTA
   static constexpr int STAGE_BYTES = CG2 ? (X3 ? 2 * A_TILE_BYTES + 2 * W_PART : A_TILE_BYTES + W_PART)
                                          : A_TILE_BYTES + NSLOT * W_TILE_BYTES;
@@ -102,12 +105,18 @@ struct LinCfg {
   // per epilogue warp: box A (4 KB: fp32 32x32 output box / rotary cos), box B (4 KB: 16-bit 32x64 box, hi or
   // fp16), box C (4 KB: rotary sin, or the dense 32x32 bf16 "lo" box).  The LayerNorm variant has no box A.
   // (NSLOT == 2: one dense 32x32 bf16 box, 2 KB, shared by the hi and lo images)
+  // (NSLOT == 2: dense 32x32 bf16 boxes of 2 KB: one shared by the hi and lo images, or -- pair kernels -- one each)
   static constexpr int WARP_BYTES = NSLOT == 1 ? 3 * 4096 : 2048;
+  // LayerNorm variant: 16 of the 64 slot-0 values every epilogue thread keeps across the MMAs of slot 1 live in shared
+  // memory, the other 48 in registers (576 threads leave 96 registers per thread); the single-CTA debug variant has no
+  // room for it next to its 80 KB stages and spills instead
+  static constexpr int STASH_SMEM = (NSLOT == 2 && CG2) ? 16 : 0;
+  static constexpr int STASH_BYTES = STASH_SMEM * EW * 32 * 4;
   static constexpr int BOXB_OFF = NSLOT == 1 ? 4096 : 0;
   static constexpr int BOXC_OFF = NSLOT == 1 ? 8192 : 0;
   static constexpr int VEC_BYTES = (NSLOT == 1 ? 1 : 3) * COLS * 4;     // bias (| ln gamma | ln beta)
   static constexpr int LNP_BYTES = NSLOT == 1 ? 0 : 128 * GROUPS * 2 * 8;  // LayerNorm partial (mean, M2) per row, slot and column group
-  static constexpr int FIXED_BYTES = EW * WARP_BYTES + VEC_BYTES + LNP_BYTES + 512 + 1024;
+  static constexpr int FIXED_BYTES = EW * WARP_BYTES + VEC_BYTES + LNP_BYTES + STASH_BYTES + 512 + 1024;
   static constexpr int SMEM_MAX = 232448;  // 227 KB per CTA
   static constexpr int FIT = (SMEM_MAX - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = FIT > 6 ? 6 : FIT;
@@ -206,7 +215,8 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
   float* s_gamma = s_bias + (NSLOT == 1 ? 0 : COLS);       // LayerNorm variant only
   float* s_beta = s_gamma + (NSLOT == 1 ? 0 : COLS);
   float2* s_lnp = reinterpret_cast<float2*>(s_bias + C::VEC_BYTES / 4);  // [GROUPS][128 rows]
-  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_lnp) + C::LNP_BYTES);
+  float* s_stash = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_lnp) + C::LNP_BYTES);  // [STASH_SMEM][epilogue threads]
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_stash) + C::STASH_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
   uint64_t* acc_empty = acc_full + NBUF;
@@ -237,8 +247,8 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
     if (CG2) tmem_alloc_cg2<512>(tmem_slot);
     else tmem_alloc<512>(tmem_slot);
   }
-  if (EPI == TEPI_LN_GELU && warp >= 2) {
-    for (int i = threadIdx.x - 64; i < COLS; i += EPI_WARPS * 32) { s_gamma[i] = p.ln_g[i]; s_beta[i] = p.ln_b[i]; }
+  if (EPI == TEPI_LN_GELU && warp >= C::CTRL) {
+    for (int i = threadIdx.x - C::CTRL * 32; i < COLS; i += EPI_WARPS * 32) { s_gamma[i] = p.ln_g[i]; s_beta[i] = p.ln_b[i]; }
   }
   tc_fence_before();
   __syncthreads();
@@ -314,6 +324,10 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc(CG2 ? 2 * BM : BM, (CG2 && p.mma_n) ? p.mma_n : BN, true);
     int g = 0, li = 0;  // li: index among this CTA's live tiles
+#ifdef LG_TC_TRACE
+    long long trm[8][4];
+    const bool tracing = EPI == TEPI_LN_GELU && blockIdx.x == 0;
+#endif
     TileWalk<MC> walk(total_tiles, n_tiles);
     TileInfo ti;
     bool store;
@@ -336,8 +350,14 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
           mbar_wait_cluster(&acc_empty[it / p.kb_total], par ^ 1, p.dbg, 20, li);
           tc_fence_after();
         }
+#ifdef LG_TC_TRACE
+        if (tracing && li < 8 && it % p.kb_total == 0) trm[li][(it / p.kb_total) * 2] = clock64();  // slot free
+#endif
         mbar_wait(&full[stage], round & 1, p.dbg, 18, it);
         tc_fence_after();
+#ifdef LG_TC_TRACE
+        if (tracing && li < 8 && it % p.kb_total == p.kb_total - 1) trm[li][(it / p.kb_total) * 2 + 1] = clock64();  // last stage of the slot arrived
+#endif
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           if (CG2) {
@@ -379,16 +399,21 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
       }
       ++li;
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue (8 warps)
+#ifdef LG_TC_TRACE
+    if (tracing && lane == 0 && (!CG2 || rank == 0))
+      for (int i = 0; i < li && i < 8; ++i)
+        printf("TRM tile %d slot0_free %lld slot0_last_full %lld slot1_free %lld slot1_last_full %lld\n", i, trm[i][0], trm[i][1], trm[i][2], trm[i][3]);
+#endif
+  } else if (warp >= C::CTRL) {
+    // ------------------------------------------------------------------ epilogue (8 or 16 warps)
     // Everything stays in the row-per-thread layout tcgen05.ld delivers: results are packed into 32-row x
     // 128-byte shared-memory boxes in the 128B-swizzle pattern and leave through TMA stores; the fp32
     // residual and the rotary tables arrive the same way through TMA loads.  No per-lane global traffic.
-    const int ew = warp - 2;
+    const int ew = warp - C::CTRL;
     const int quarter = warp % 4;                 // TMEM lane group this warp may read
     const int half = ew / 4;                      // which column group of the tile this warp owns
     constexpr int HCOLS = COLS / C::GROUPS;       // columns per warp (128)
-    const int te = threadIdx.x - 64;              // index among the epilogue threads
+    const int te = threadIdx.x - C::CTRL * 32;    // index among the epilogue threads
     uint8_t* wsm = epi_smem + ew * C::WARP_BYTES;
     uint8_t* boxA = wsm;                          // fp32 box / cos (NSLOT == 1 only)
     uint8_t* boxB = wsm + C::BOXB_OFF;            // 16-bit box: 32 rows x 64 elements, swizzled
@@ -401,6 +426,10 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
     uint8_t* crow_lo = boxC + lane * 64;          // as a dense 64-byte row (lo)
     uint32_t ld_phase = 0;
     int li = 0;
+#ifdef LG_TC_TRACE
+    long long tre[8][6];
+    const bool tracing = EPI == TEPI_LN_GELU && blockIdx.x == 0 && ew == 0;
+#endif
     TileWalk<MC> walk(total_tiles, n_tiles);
     TileInfo ti;
     bool store;
@@ -441,36 +470,93 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
       if (EPI == TEPI_LN_GELU) {
         // ---------------------------------------------------------------- LayerNorm(512) + GELU, slot by slot
         // Warp (quarter, group g) owns rows 32 quarter .. +31 and columns 64 g .. +63 of BOTH 256-column slots.
-        // Statistics of slot 0 are taken while the tensor core still works on slot 1; after the merge slot 0 is
-        // normalised and handed back first, so the MMAs of the next tile's slot 0 overlap the normalisation of slot 1.
+        // Slot 0 is complete half an MMA phase before slot 1 (the slot is the outer loop of the K ring).  Its statistics
+        // pass keeps the 64 biased values of every thread in REGISTERS and hands the slot back at once, so the tensor
+        // pipe starts the next tile's slot 0 the moment this tile's slot 1 is complete: the whole normalisation (slot 0
+        // from registers, then slot 1 from TMEM) runs under the next tile's MMAs.  (In-kernel clock trace before this
+        // change, cycles per tile: MMAs 21.4 k + 15.5 k, then 15.8 k with the tensor pipe idle -- drain + statistics 3.4 k,
+        // normalisation of slot 0 out of TMEM 11.6 k -- before the next tile could start.)
         constexpr int GC = 64;
         const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        uint32_t raw[32];
-        for (int sl = 0; sl < 2; ++sl) {
-          mbar_wait(&acc_full[sl], par, p.dbg, 19, li);
+        constexpr int SREG = GC - C::STASH_SMEM;  // slot-0 values of this thread kept in registers (the rest: s_stash)
+        uint32_t stash_u[GC];  // raw accumulators, then + bias, then the finished GELU values (bit patterns)
+        float* stash = reinterpret_cast<float*>(stash_u);
+        float* my_stash = s_stash + te;  // element i of this thread: my_stash[i * EPI_WARPS * 32] (conflict-free)
+        {
+          mbar_wait(&acc_full[0], par, p.dbg, 19, li);
           tc_fence_after();
+#ifdef LG_TC_TRACE
+          if (tracing && li < 8) tre[li][0] = clock64();
+#endif
+          float sh = 0.f, s1 = 0.f, s2 = 0.f;
+          uint32_t tail[16];
+          tmem_ld32(tq + half * GC, *reinterpret_cast<uint32_t(*)[32]>(stash_u));
+          if constexpr (SREG == GC) {
+            tmem_ld32(tq + half * GC + 32, *reinterpret_cast<uint32_t(*)[32]>(stash_u + 32));
+          } else {
+            tmem_ld16(tq + half * GC + 32, *reinterpret_cast<uint32_t(*)[16]>(stash_u + 32));
+            tmem_ld16(tq + half * GC + 48, tail);
+          }
+          tmem_ld_wait();
+          release_acc(0);  // slot 0 lives in registers now: the next tile's MMAs may overwrite it
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + half * GC);
+#pragma unroll
+          for (int j4 = 0; j4 < GC / 4; ++j4) {
+            const float4 bb = b4[j4];
+            float v0, v1, v2, v3;
+            if (4 * j4 < SREG) {
+              v0 = stash[(4 * j4) % SREG] + bb.x; v1 = stash[(4 * j4 + 1) % SREG] + bb.y;
+              v2 = stash[(4 * j4 + 2) % SREG] + bb.z; v3 = stash[(4 * j4 + 3) % SREG] + bb.w;
+              stash[(4 * j4) % SREG] = v0; stash[(4 * j4 + 1) % SREG] = v1; stash[(4 * j4 + 2) % SREG] = v2; stash[(4 * j4 + 3) % SREG] = v3;
+            } else {
+              const int t4 = (4 * j4 - SREG) % 16;
+              v0 = __uint_as_float(tail[t4]) + bb.x; v1 = __uint_as_float(tail[t4 + 1]) + bb.y;
+              v2 = __uint_as_float(tail[t4 + 2]) + bb.z; v3 = __uint_as_float(tail[t4 + 3]) + bb.w;
+              my_stash[(t4) * EPI_WARPS * 32] = v0; my_stash[(t4 + 1) * EPI_WARPS * 32] = v1;
+              my_stash[(t4 + 2) * EPI_WARPS * 32] = v2; my_stash[(t4 + 3) * EPI_WARPS * 32] = v3;
+            }
+            if (j4 == 0) sh = v0;  // shift by the first element: cancellation-free E[(v-sh)^2]
+            const float d0 = v0 - sh, d1 = v1 - sh, d2 = v2 - sh, d3 = v3 - sh;
+            s1 += (d0 + d1) + (d2 + d3);
+            s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
+          }
+          // this group: mean_g = sh + s1/GC, M2_g = sum (v - mean_g)^2 = s2 - s1^2/GC (shifted -> no cancellation)
+          s_lnp[half * 128 + quarter * 32 + lane] = make_float2(sh + s1 * (1.f / GC), s2 - s1 * s1 * (1.f / GC));
+        }
+        {
+          mbar_wait(&acc_full[1], par, p.dbg, 19, li);
+          tc_fence_after();
+#ifdef LG_TC_TRACE
+          if (tracing && li < 8) tre[li][1] = clock64();
+#endif
           float sh = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-          for (int c0 = 0; c0 < GC; c0 += 32) {
-            const int tcol = sl * BN + half * GC + c0;
-            tmem_ld32(tq + tcol, raw);
+          for (int c0 = 0; c0 < GC; c0 += 16) {
+            const int tcol = BN + half * GC + c0;
+            uint32_t raw[16];
+            tmem_ld16(tq + tcol, raw);
             tmem_ld_wait();
             const float4* b4 = reinterpret_cast<const float4*>(s_bias + tcol);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
+            for (int j4 = 0; j4 < 4; ++j4) {
               const float4 bb = b4[j4];
               const float v0 = __uint_as_float(raw[4 * j4]) + bb.x, v1 = __uint_as_float(raw[4 * j4 + 1]) + bb.y;
               const float v2 = __uint_as_float(raw[4 * j4 + 2]) + bb.z, v3 = __uint_as_float(raw[4 * j4 + 3]) + bb.w;
-              if (c0 == 0 && j4 == 0) sh = v0;  // shift by the first element: cancellation-free E[(v-sh)^2]
+              if (c0 == 0 && j4 == 0) sh = v0;
               const float d0 = v0 - sh, d1 = v1 - sh, d2 = v2 - sh, d3 = v3 - sh;
               s1 += (d0 + d1) + (d2 + d3);
               s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
             }
           }
-          // this group: mean_g = sh + s1/GC, M2_g = sum (v - mean_g)^2 = s2 - s1^2/GC (shifted -> no cancellation)
-          s_lnp[(sl * C::GROUPS + half) * 128 + quarter * 32 + lane] = make_float2(sh + s1 * (1.f / GC), s2 - s1 * s1 * (1.f / GC));
+          s_lnp[(C::GROUPS + half) * 128 + quarter * 32 + lane] = make_float2(sh + s1 * (1.f / GC), s2 - s1 * s1 * (1.f / GC));
         }
+#ifdef LG_TC_TRACE
+        if (tracing && li < 8) tre[li][2] = clock64();
+#endif
         epi_bar();
+#ifdef LG_TC_TRACE
+        if (tracing && li < 8) tre[li][3] = clock64();
+#endif
         // equal-sized groups merge with Chan's formula: mean = avg(mean_g), M2 = sum M2_g + GC * sum (mean_g - mean)^2
         float msum = 0.f, m2 = 0.f;
 #pragma unroll
@@ -481,68 +567,101 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
         for (int g = 0; g < 2 * C::GROUPS; ++g) { const float dm = s_lnp[g * 128 + quarter * 32 + lane].x - mean; dev = fmaf(dm, dm, dev); }
         const float rstd = rsqrtf(fmaxf((m2 + dev * GC) * (1.f / COLS), 0.f) + 1e-5f);
         const bool haslo = p.out_l != nullptr;
-        uint8_t* box = epi_smem + ew * C::WARP_BYTES;  // one dense 32 x 32 bf16 box per warp (hi, then lo)
-        uint8_t* brow32 = box + lane * 64;
+        // per warp: one dense 32 x 32 bf16 box for the hi image and (pair kernels) a second one for the lo image, so that a
+        // box is rewritten while the bulk store of the OTHER one is still reading (wait_group.read 1)
+        uint8_t* box_hi = epi_smem + ew * C::WARP_BYTES;
+        uint8_t* box_lo = box_hi + (C::WARP_BYTES > 2048 ? 2048 : 0);
+        constexpr bool two_boxes = C::WARP_BYTES > 2048;
         const int grow_w2 = (int)ti.grow0 + quarter * 32;
-        for (int sl = 0; sl < 2; ++sl) {
-#pragma unroll 1
-          for (int c0 = 0; c0 < GC; c0 += 32) {
-            const int tcol = sl * BN + half * GC + c0;
-            tmem_ld32(tq + tcol, raw);
-            if (lane == 0) tma_store_wait_read();        // the box may be rewritten
-            tmem_ld_wait();
+        // exact (erf) GELU of the normalised value; erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): 1 MUFU.RCP + 1 MUFU.EX2
+        auto ln_gelu = [&](float xb, float g, float be) -> float {
+          const float y = fmaf((xb - mean) * rstd, g, be);
+          const float z = fabsf(y) * 0.70710678118654752f;
+          const float tt = rcp_approx(fmaf(0.3275911f, z, 1.f));
+          float pl = fmaf(1.061405429f, tt, -1.453152027f);
+          pl = fmaf(pl, tt, 1.421413741f); pl = fmaf(pl, tt, -0.284496736f); pl = fmaf(pl, tt, 0.254829592f);
+          const float ez = ex2_approx(-1.4426950408889634f * z * z);
+          const float erf_abs = fmaf(-pl * tt, ez, 1.f);
+          const float hy = 0.5f * y;
+          return fmaf(copysignf(erf_abs, y), hy, hy);
+        };
+        // v[0..31]: 32 finished columns of this thread's row -> hi (and lo) bf16 images through the box(es)
+        auto store32 = [&](const float* v, int tcol) {
+          for (int pass = 0; pass < (haslo ? 2 : 1); ++pass) {
+            uint8_t* box = pass == 0 ? box_hi : box_lo;
+            if (lane == 0) { if (two_boxes && haslo) tma_store_wait_read1(); else tma_store_wait_read(); }  // the box may be rewritten
             __syncwarp();
-            const float4* b4 = reinterpret_cast<const float4*>(s_bias + tcol);
-            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + tcol);
-            const float4* e4 = reinterpret_cast<const float4*>(s_beta + tcol);
-            float v[32];
+            uint8_t* brow32 = box + lane * 64;
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bb = b4[j4], g = g4[j4], be = e4[j4];
-              const float xin[4] = {__uint_as_float(raw[4 * j4]) + bb.x, __uint_as_float(raw[4 * j4 + 1]) + bb.y,
-                                    __uint_as_float(raw[4 * j4 + 2]) + bb.z, __uint_as_float(raw[4 * j4 + 3]) + bb.w};
-              const float gg[4] = {g.x, g.y, g.z, g.w}, bt[4] = {be.x, be.y, be.z, be.w};
+            for (int j8 = 0; j8 < 4; ++j8) {
+              uint32_t w[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float y = fmaf((xin[e] - mean) * rstd, gg[e], bt[e]);
-                // exact (erf) GELU; erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): 1 MUFU.RCP + 1 MUFU.EX2
-                const float z = fabsf(y) * 0.70710678118654752f;
-                const float tt = rcp_approx(fmaf(0.3275911f, z, 1.f));
-                float pl = fmaf(1.061405429f, tt, -1.453152027f);
-                pl = fmaf(pl, tt, 1.421413741f); pl = fmaf(pl, tt, -0.284496736f); pl = fmaf(pl, tt, 0.254829592f);
-                const float ez = ex2_approx(-1.4426950408889634f * z * z);
-                const float erf_abs = fmaf(-pl * tt, ez, 1.f);
-                const float hy = 0.5f * y;
-                v[4 * j4 + e] = fmaf(copysignf(erf_abs, y), hy, hy);
+                const float a = v[8 * j8 + 2 * e], b = v[8 * j8 + 2 * e + 1];
+                const uint32_t hi = pack_bf16x2(a, b);
+                w[e] = pass == 0 ? hi : pack_bf16x2_lo(a, b, hi);
               }
+              *reinterpret_cast<uint4*>(brow32 + (j8 << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            for (int pass = 0; pass < (haslo ? 2 : 1); ++pass) {
-              if (pass == 1) {
-                if (lane == 0) tma_store_wait_read();
-                __syncwarp();
-              }
-#pragma unroll
-              for (int j8 = 0; j8 < 4; ++j8) {
-                uint32_t w[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float a = v[8 * j8 + 2 * e], b = v[8 * j8 + 2 * e + 1];
-                  const uint32_t hi = pack_bf16x2(a, b);
-                  w[e] = pass == 0 ? hi : pack_bf16x2_lo(a, b, hi);
-                }
-                *reinterpret_cast<uint4*>(brow32 + (j8 << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-              }
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(pass == 0 ? &p.o_h32 : &p.o_l32, box, tcol, grow_w2);
-                tma_store_commit();
-              }
-            }
+            fence_proxy_async();
             __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(pass == 0 ? &p.o_h32 : &p.o_l32, box, tcol, grow_w2);
+              tma_store_commit();
+            }
           }
-          release_acc(sl);  // slot sl of this tile is drained: the next tile's MMAs may overwrite it
+        };
+        // slot 0 out of the registers (and the shared-memory part of the stash)
+#pragma unroll
+        for (int c0 = 0; c0 < GC; c0 += 32) {
+          const int tcol = half * GC + c0;
+          const float4* g4 = reinterpret_cast<const float4*>(s_gamma + tcol);
+          const float4* e4 = reinterpret_cast<const float4*>(s_beta + tcol);
+          float* v = stash + c0;  // in place: every value is read once
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 g = g4[j4], be = e4[j4];
+            const int i0 = c0 + 4 * j4;
+            float x0, x1, x2, x3;
+            if (i0 < SREG) { x0 = stash[i0]; x1 = stash[i0 + 1]; x2 = stash[i0 + 2]; x3 = stash[i0 + 3]; }
+            else {
+              const int t4 = (i0 - SREG) % 16;
+              x0 = my_stash[t4 * EPI_WARPS * 32]; x1 = my_stash[(t4 + 1) * EPI_WARPS * 32];
+              x2 = my_stash[(t4 + 2) * EPI_WARPS * 32]; x3 = my_stash[(t4 + 3) * EPI_WARPS * 32];
+            }
+            v[4 * j4] = ln_gelu(x0, g.x, be.x); v[4 * j4 + 1] = ln_gelu(x1, g.y, be.y);
+            v[4 * j4 + 2] = ln_gelu(x2, g.z, be.z); v[4 * j4 + 3] = ln_gelu(x3, g.w, be.w);
+          }
+          store32(v, tcol);
         }
+#ifdef LG_TC_TRACE
+        if (tracing && li < 8) tre[li][4] = clock64();
+#endif
+        // slot 1 out of TMEM
+#pragma unroll 1
+        for (int c0 = 0; c0 < GC; c0 += 32) {
+          const int tcol = BN + half * GC + c0;
+          uint32_t raw[32];
+          tmem_ld32(tq + tcol, raw);
+          tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + tcol);
+          const float4* g4 = reinterpret_cast<const float4*>(s_gamma + tcol);
+          const float4* e4 = reinterpret_cast<const float4*>(s_beta + tcol);
+          float v[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = b4[j4], g = g4[j4], be = e4[j4];
+            v[4 * j4] = ln_gelu(__uint_as_float(raw[4 * j4]) + bb.x, g.x, be.x);
+            v[4 * j4 + 1] = ln_gelu(__uint_as_float(raw[4 * j4 + 1]) + bb.y, g.y, be.y);
+            v[4 * j4 + 2] = ln_gelu(__uint_as_float(raw[4 * j4 + 2]) + bb.z, g.z, be.z);
+            v[4 * j4 + 3] = ln_gelu(__uint_as_float(raw[4 * j4 + 3]) + bb.w, g.w, be.w);
+          }
+          if (c0 + 32 >= GC) release_acc(1);  // the last TMEM read of slot 1 is done: the next tile's MMAs may overwrite it
+          store32(v, tcol);
+        }
+#ifdef LG_TC_TRACE
+        if (tracing && li < 8) tre[li][5] = clock64();
+#endif
         ++li;
         continue;
       }
@@ -770,6 +889,11 @@ __global__ void __launch_bounds__(LinCfg<NSLOT, CG2, X3>::THREADS, 1) tc_linear_
       ++li;
     }
     if (lane == 0) tma_store_wait_all();
+#ifdef LG_TC_TRACE
+    if (tracing && lane == 0)
+      for (int i = 0; i < li && i < 8; ++i)
+        printf("TRE tile %d full0 %lld full1 %lld stats %lld merged %lld rel0 %lld rel1 %lld\n", i, tre[i][0], tre[i][1], tre[i][2], tre[i][3], tre[i][4], tre[i][5]);
+#endif
   }
   tc_fence_before();
   __syncthreads();
