@@ -5,8 +5,10 @@
 //   S_t = Q_t K_j^T      tcgen05.mma  M=128 N=64 K=64    operands in shared memory (TMA, 128B swizzle)
 //   P_t = exp2(c S_t - c m_t)   softmax warpgroup t: TMEM -> registers -> fp16 -> TMEM (in place over S_t)
 //   O_t += P_t V_j       tcgen05.mma  M=128 N=64 K=64    A = P_t from TMEM, B = V^T tile in shared memory
-// O(N) softmax: running max with lazy rescaling (O is only rescaled when the row max grows by more than 2^8),
-// the denominator is summed in registers (packed f32x2 adds), one division at the end.
+// O(N) softmax against a lazily moved reference maximum: a block's exponentials are taken against the reference of the
+// earlier blocks WITHOUT looking for the row maximum first; the block's row sum (needed anyway) shows whether any P left the
+// safe fp16 range, and only then the true maximum is taken, O / l are rescaled and the block is redone.  The denominator is
+// summed in registers (packed f32x2 adds), one division at the end.
 // 256 TMEM columns and ~100 KB of shared memory per CTA, so TWO CTAs are resident per SM: four softmax warps per
 // scheduler hide the TMEM-load / barrier latencies of a block.  TMEM map: S0 0-63 | S1 64-127 | O0 128-191 | O1 192-255.
 // Warp roles (384 threads = 3 warpgroups): warpgroup 0 = {warp 0 TMA producer, warp 1 TMEM owner + MMA issuer of
@@ -34,7 +36,6 @@ struct AttnParams {
   __nv_bfloat16* ctxh; __nv_bfloat16* ctxl;
   int kv_shift;
   int rows_per_cta;  // 256 (two query tiles per CTA) or 128 (one: small problems that would not fill the SMs)
-  float rescale_log2;  // lazy rescaling: O / l are rescaled only when the row maximum grows by more than 2^rescale_log2
   int pingpong;      // alternate the exponential phases of the CTA's two query tiles (LG_ATTN_NO_PINGPONG=1 switches it off)
   SeqState st;
   unsigned int* dbg;
@@ -220,6 +221,34 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
         uint32_t sv[2][32];
         const bool pingpong = nt == 2 && p.pingpong;
         if (pingpong && t == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");  // tile 0 goes first
+        // P = exp2(c s - c m_used) of one 64-key block: scale-and-shift and row sum as packed f32x2 operations, P stored
+        // in place over S; returns the row sum of the block.  (A degree-3 Cody-Waite polynomial for 12 - 50 % of the
+        // exponentials on the FMA pipe, packed f32x2, was measured on B200: 405 - 468 us per launch against 412 with
+        // every exponential on the MUFU -- no gain.)
+        auto exp_block = [&](float m) -> float {
+          const uint64_t sc2 = pack2(SCALE_LOG2, SCALE_LOG2);
+          const float nmc = -m * SCALE_LOG2;
+          const uint64_t nm2 = pack2(nmc, nmc);
+          uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float x0, x1;
+              unpack2(fma2(pack2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2), x0, x1);
+              const float e0 = ex2(x0), e1 = ex2(x1);
+              if (i & 1) lb = add2(lb, pack2(e0, e1));
+              else la = add2(la, pack2(e0, e1));
+              const __half2 hh = __floats2half2_rn(e0, e1);
+              pk[i] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            tmem_st16(ts + c * 16, pk);
+          }
+          float a0, a1;
+          unpack2(add2(la, lb), a0, a1);
+          return a0 + a1;
+        };
         for (int j = 0; j < nkv; ++j) {
           mbar_wait_sleep(&s_full[t], j & 1, p.dbg, 6, j * 2 + t);
           tc_fence_after();
@@ -234,76 +263,55 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
               for (int i = 0; i < 32; ++i)
                 if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;
           }
-          float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              mx0 = max3(mx0, __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
-              mx1 = max3(mx1, __uint_as_float(sv[c][i + 2]), __uint_as_float(sv[c][i + 3]));
-            }
-          const float mx = fmaxf(mx0, mx1);
-          float alpha = 1.f;
-          bool need = false;
-          if (mx > m_used) {
-            if (m_used == -INFINITY) { m_used = mx; }
-            else if ((mx - m_used) * SCALE_LOG2 > p.rescale_log2) { alpha = ex2((m_used - mx) * SCALE_LOG2); m_used = mx; need = true; }
-          }
-          if (__any_sync(0xffffffffu, need)) {  // S_t(j) was issued after P_t(j-1) V: that MMA has retired
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t o16[16];
-              tmem_ld16(to + c * 16, o16);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o16[i] = __float_as_uint(__uint_as_float(o16[i]) * alpha);
-              tmem_st16(to + c * 16, o16);
-            }
-            l *= alpha;
-          }
+          // Fast path: NO row maximum.  The exponentials are taken against the reference maximum m_used of the earlier
+          // blocks and the block's row sum (needed anyway) tells whether that was safe: sum <= 2^14 means every P <= 2^14,
+          // far inside fp16; anything else (a larger value, +inf) sends the WARP through the slow path below, which takes
+          // the true row maximum, rescales O / l and redoes the block.  m_used only moves when it has to, so the slow
+          // path runs in the first block and a few more per row (the row-maximum pass cost 430 - 780 cycles of the ~2900
+          // per block in the clock trace, on the critical chain of the tile).
           // Ping-pong between the two query tiles of the CTA (named barriers 2 / 3): the exponentials of tile t run
           // while tile 1-t waits for its MMAs, and vice versa (measured on B200: 410 us per launch against 427 without).
-          // In-kernel clock trace of one tile at B=32, N=2048 (cycles per 64-key block, ~2900 in total): wait for S
-          // 580 (P arrival -> MMA warp wake 160, PV + next QK^T issue and execution behind the other tiles' MMAs
-          // 480), TMEM load 155, row max (+ lazy rescale) 430-780, exponentials 880-1100 (512 alone: the MUFU unit of
-          // a scheduler is shared by four tiles), P store + arrive 190.  Tried and measured slower: 32-key blocks
-          // with double-buffered S (473 us: the per-block fixed costs double); exponentials started speculatively
-          // against the previous reference maximum with the row maximum taken in the same loop (7.70 vs 7.50 ms of
-          // attention per step: redone blocks and the longer loop body cost more than the shorter chain saves); P handed
-          // to the tensor pipe through shared memory (128B-swizzled A tile, fence.proxy.async) so that S_t is free once
-          // it is in registers and Q K_{j+1}^T overlaps block j's exponentials (8.47 vs 7.51 ms: the chain no longer
-          // waits for S, but every P V then reads its 16 KB A operand from shared memory on top of the 16 KB Q tile each
-          // Q K^T re-reads, 64 KB per tile and block against the SM's 128 B/clk, and the P stores cost more than
-          // tcgen05.st).
-          if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(2 + t) : "memory");
-          // P = exp2(c s - c m): the scale-and-shift and the row sum run as packed f32x2 operations
-          const uint64_t sc2 = pack2(SCALE_LOG2, SCALE_LOG2);
-          const float nmc = -m_used * SCALE_LOG2;
-          const uint64_t nm2 = pack2(nmc, nmc);
-          uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
+          float bsum = 0.f;
+          bool slow = j == 0;
+          if (j > 0) {
+            if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(2 + t) : "memory");
+            bsum = exp_block(m_used);
+            if (pingpong && !(t == 1 && j + 1 == nkv)) asm volatile("bar.arrive %0, 256;" ::"r"(3 - t) : "memory");  // the other tile's turn
+            slow = !(bsum <= 16384.f);
+          } else if (pingpong) {
+            asm volatile("bar.sync %0, 256;" ::"r"(2 + t) : "memory");
+            if (!(t == 1 && j + 1 == nkv)) asm volatile("bar.arrive %0, 256;" ::"r"(3 - t) : "memory");
+          }
+          if (__any_sync(0xffffffffu, slow)) {
+            float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t pk[16];
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              // (a degree-3 Cody-Waite polynomial for 12 - 50 % of the exponentials on the FMA pipe, packed f32x2, was
-              //  measured on B200: 405 - 468 us per launch against 412 with every exponential on the MUFU -- no gain)
-              float x0, x1;
-              unpack2(fma2(pack2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2), x0, x1);
-              const float e0 = ex2(x0), e1 = ex2(x1);
-              if (i & 1) lb = add2(lb, pack2(e0, e1));
-              else la = add2(la, pack2(e0, e1));
-              const __half2 hh = __floats2half2_rn(e0, e1);
-              pk[i] = *reinterpret_cast<const uint32_t*>(&hh);
+              for (int i = 0; i < 32; i += 4) {
+                mx0 = max3(mx0, __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+                mx1 = max3(mx1, __uint_as_float(sv[c][i + 2]), __uint_as_float(sv[c][i + 3]));
+              }
+            const float mx = fmaxf(mx0, mx1);
+            float alpha = 1.f;
+            if (slow && mx > m_used) {
+              if (m_used != -INFINITY) alpha = ex2((m_used - mx) * SCALE_LOG2);
+              m_used = mx;
             }
-            tmem_st16(ts + c * 16, pk);
+            if (j > 0) {  // S_t(j) was issued after P_t(j-1) V: that MMA has retired, O_t may be rescaled
+#pragma unroll 1
+              for (int c = 0; c < 4; ++c) {
+                uint32_t o16[16];
+                tmem_ld16(to + c * 16, o16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o16[i] = __float_as_uint(__uint_as_float(o16[i]) * alpha);
+                tmem_st16(to + c * 16, o16);
+              }
+              l *= alpha;
+            }
+            bsum = exp_block(m_used);  // lanes whose reference did not move reproduce their block bit for bit
           }
-          if (pingpong && !(t == 1 && j + 1 == nkv)) asm volatile("bar.arrive %0, 256;" ::"r"(3 - t) : "memory");  // the other tile's turn
-          {
-            float a0, a1;
-            unpack2(add2(la, lb), a0, a1);
-            l += a0 + a1;
-          }
+          l += bsum;
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&p_full[t]);
@@ -372,9 +380,6 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
   p.ctxh = b.ctxh; p.ctxl = b.ctxl; p.kv_shift = kv_shift; p.st = st; p.dbg = h->tc.dbg;
   dim3 grid((st.Lp + 2 * QT - 1) / (2 * QT), LG_HEADS, st.S);
   p.rows_per_cta = 2 * QT;
-  // P = 2^x with x <= rescale_log2 stays far inside fp16 (65504 = 2^16) and the fp32 accumulators
-  static const float rescale = getenv("LG_ATTN_RESCALE_LOG2") ? (float)atof(getenv("LG_ATTN_RESCALE_LOG2")) : 8.f;
-  p.rescale_log2 = rescale;
   static const bool no_pp = getenv("LG_ATTN_NO_PINGPONG") && atoi(getenv("LG_ATTN_NO_PINGPONG")) != 0;
   p.pingpong = no_pp ? 0 : 1;
   if ((long)grid.x * grid.y * grid.z < 2 * lg_num_sms()) {  // fewer CTAs than resident slots: one query tile per CTA instead
