@@ -102,6 +102,141 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+// One softmax warpgroup: query tile t (of nt in this CTA), one query row per thread.  ts / to: TMEM addresses of S_t / O_t
+// (lane offset of this warp included); r: global row of this thread, off: its offset in the context images.
+__device__ __forceinline__ void softmax_tile(const AttnParams& p, int t, int nt, uint32_t ts, uint32_t to, uint64_t* s_full,
+                                             uint64_t* p_full, uint64_t* o_final, int nkv, int len_kv, int len_q, int r, long off) {
+        float m_used = -INFINITY, l = 0.f;
+        uint32_t sv[2][32];
+        // token ring over the CTA's query tiles (named barrier 2 + tile index): tile t takes its exponentials when tile
+        // t-1 has finished its own; the last tile hands the first token to tile 0.  (Measured with FOUR tiles in one
+        // 640-thread CTA per SM, all 512 TMEM columns, one MMA-issuer warp, ring of four: 8.13 ms of attention per step
+        // against 7.40 with two independent two-tile CTAs per SM -- one tile at a time does not keep the MUFU pipe fed,
+        // a single warp per scheduler leaves issue bubbles that a second tile's exponentials fill.)
+        const bool pingpong = nt > 1 && p.pingpong;
+        const int bar_self = 2 + t, bar_next = 2 + (t + 1 == nt ? 0 : t + 1);
+        const bool ring_last = t + 1 == nt;
+        if (pingpong && ring_last) asm volatile("bar.arrive 2, 256;" ::: "memory");  // tile 0 goes first
+        // P = exp2(c s - c m_used) of one 64-key block: scale-and-shift and row sum as packed f32x2 operations, P stored
+        // in place over S; returns the row sum of the block.  (A degree-3 Cody-Waite polynomial for 12 - 50 % of the
+        // exponentials on the FMA pipe, packed f32x2, was measured on B200: 405 - 468 us per launch against 412 with
+        // every exponential on the MUFU -- no gain.)
+        auto exp_block = [&](float m) -> float {
+          const uint64_t sc2 = pack2(SCALE_LOG2, SCALE_LOG2);
+          const float nmc = -m * SCALE_LOG2;
+          const uint64_t nm2 = pack2(nmc, nmc);
+          uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float x0, x1;
+              unpack2(fma2(pack2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2), x0, x1);
+              const float e0 = ex2(x0), e1 = ex2(x1);
+              if (i & 1) lb = add2(lb, pack2(e0, e1));
+              else la = add2(la, pack2(e0, e1));
+              const __half2 hh = __floats2half2_rn(e0, e1);
+              pk[i] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            tmem_st16(ts + c * 16, pk);
+          }
+          float a0, a1;
+          unpack2(add2(la, lb), a0, a1);
+          return a0 + a1;
+        };
+        for (int j = 0; j < nkv; ++j) {
+          mbar_wait_sleep(&s_full[t], j & 1, p.dbg, 6, j * 2 + t);
+          tc_fence_after();
+          const int valid = len_kv - j * KB;
+          tmem_ld32(ts, sv[0]);
+          tmem_ld32(ts + 32, sv[1]);
+          tmem_ld_wait();
+          if (valid < KB) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;
+          }
+          // Fast path: NO row maximum.  The exponentials are taken against the reference maximum m_used of the earlier
+          // blocks and the block's row sum (needed anyway) tells whether that was safe: sum <= 2^14 means every P <= 2^14,
+          // far inside fp16; anything else (a larger value, +inf) sends the WARP through the slow path below, which takes
+          // the true row maximum, rescales O / l and redoes the block.  m_used only moves when it has to, so the slow
+          // path runs in the first block and a few more per row (the row-maximum pass cost 430 - 780 cycles of the ~2900
+          // per block in the clock trace, on the critical chain of the tile).
+          // Ping-pong between the two query tiles of the CTA (named barriers 2 / 3): the exponentials of tile t run
+          // while tile 1-t waits for its MMAs, and vice versa (measured on B200: 410 us per launch against 427 without).
+          float bsum = 0.f;
+          bool slow = j == 0;
+          if (j > 0) {
+            if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(bar_self) : "memory");
+            bsum = exp_block(m_used);
+            if (pingpong && !(ring_last && j + 1 == nkv)) asm volatile("bar.arrive %0, 256;" ::"r"(bar_next) : "memory");  // the other tile's turn
+            slow = !(bsum <= 16384.f);
+          } else if (pingpong) {
+            asm volatile("bar.sync %0, 256;" ::"r"(bar_self) : "memory");
+            if (!(ring_last && j + 1 == nkv)) asm volatile("bar.arrive %0, 256;" ::"r"(bar_next) : "memory");
+          }
+          if (__any_sync(0xffffffffu, slow)) {
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                mx0 = max3(mx0, __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+                mx1 = max3(mx1, __uint_as_float(sv[c][i + 2]), __uint_as_float(sv[c][i + 3]));
+              }
+            const float mx = fmaxf(mx0, mx1);
+            float alpha = 1.f;
+            if (slow && mx > m_used) {
+              if (m_used != -INFINITY) alpha = ex2((m_used - mx) * SCALE_LOG2);
+              m_used = mx;
+            }
+            if (j > 0) {  // S_t(j) was issued after P_t(j-1) V: that MMA has retired, O_t may be rescaled
+#pragma unroll 1
+              for (int c = 0; c < 4; ++c) {
+                uint32_t o16[16];
+                tmem_ld16(to + c * 16, o16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o16[i] = __float_as_uint(__uint_as_float(o16[i]) * alpha);
+                tmem_st16(to + c * 16, o16);
+              }
+              l *= alpha;
+            }
+            bsum = exp_block(m_used);  // lanes whose reference did not move reproduce their block bit for bit
+          }
+          l += bsum;
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_full[t]);
+        }
+        mbar_wait_sleep(&o_final[t], 0, p.dbg, 8, t);
+        tc_fence_after();
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld32(to + c * 32, sv[c]);
+          tmem_ld_wait();
+          if (r < len_q) {
+            uint32_t ph[16], pl[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a = __uint_as_float(sv[c][2 * i]) * inv, b = __uint_as_float(sv[c][2 * i + 1]) * inv;
+              ph[i] = pack_bf16x2(a, b);
+              pl[i] = pack_bf16x2_lo(a, b, ph[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              reinterpret_cast<uint4*>(p.ctxh + off + c * 32)[i] = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
+              if (p.ctxl)
+                reinterpret_cast<uint4*>(p.ctxl + off + c * 32)[i] = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
+            }
+          }
+        }
+}
+
 constexpr int B_KV_STAGES = 4;
 constexpr int B_V_TILE_BYTES = 64 * 128;                      // [64 d rows][64 keys]
 constexpr int B_STAGE_BYTES = K_TILE_BYTES + B_V_TILE_BYTES;  // 16 KB
@@ -215,130 +350,8 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
     if (nkv > 0) {
       if (t < nt) {
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-        const uint32_t ts = tmem_base + lane_off + t * 64;
-        const uint32_t to = tmem_base + lane_off + 128 + t * 64;
-        float m_used = -INFINITY, l = 0.f;
-        uint32_t sv[2][32];
-        const bool pingpong = nt == 2 && p.pingpong;
-        if (pingpong && t == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");  // tile 0 goes first
-        // P = exp2(c s - c m_used) of one 64-key block: scale-and-shift and row sum as packed f32x2 operations, P stored
-        // in place over S; returns the row sum of the block.  (A degree-3 Cody-Waite polynomial for 12 - 50 % of the
-        // exponentials on the FMA pipe, packed f32x2, was measured on B200: 405 - 468 us per launch against 412 with
-        // every exponential on the MUFU -- no gain.)
-        auto exp_block = [&](float m) -> float {
-          const uint64_t sc2 = pack2(SCALE_LOG2, SCALE_LOG2);
-          const float nmc = -m * SCALE_LOG2;
-          const uint64_t nm2 = pack2(nmc, nmc);
-          uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float x0, x1;
-              unpack2(fma2(pack2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2), x0, x1);
-              const float e0 = ex2(x0), e1 = ex2(x1);
-              if (i & 1) lb = add2(lb, pack2(e0, e1));
-              else la = add2(la, pack2(e0, e1));
-              const __half2 hh = __floats2half2_rn(e0, e1);
-              pk[i] = *reinterpret_cast<const uint32_t*>(&hh);
-            }
-            tmem_st16(ts + c * 16, pk);
-          }
-          float a0, a1;
-          unpack2(add2(la, lb), a0, a1);
-          return a0 + a1;
-        };
-        for (int j = 0; j < nkv; ++j) {
-          mbar_wait_sleep(&s_full[t], j & 1, p.dbg, 6, j * 2 + t);
-          tc_fence_after();
-          const int valid = len_kv - j * KB;
-          tmem_ld32(ts, sv[0]);
-          tmem_ld32(ts + 32, sv[1]);
-          tmem_ld_wait();
-          if (valid < KB) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;
-          }
-          // Fast path: NO row maximum.  The exponentials are taken against the reference maximum m_used of the earlier
-          // blocks and the block's row sum (needed anyway) tells whether that was safe: sum <= 2^14 means every P <= 2^14,
-          // far inside fp16; anything else (a larger value, +inf) sends the WARP through the slow path below, which takes
-          // the true row maximum, rescales O / l and redoes the block.  m_used only moves when it has to, so the slow
-          // path runs in the first block and a few more per row (the row-maximum pass cost 430 - 780 cycles of the ~2900
-          // per block in the clock trace, on the critical chain of the tile).
-          // Ping-pong between the two query tiles of the CTA (named barriers 2 / 3): the exponentials of tile t run
-          // while tile 1-t waits for its MMAs, and vice versa (measured on B200: 410 us per launch against 427 without).
-          float bsum = 0.f;
-          bool slow = j == 0;
-          if (j > 0) {
-            if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(2 + t) : "memory");
-            bsum = exp_block(m_used);
-            if (pingpong && !(t == 1 && j + 1 == nkv)) asm volatile("bar.arrive %0, 256;" ::"r"(3 - t) : "memory");  // the other tile's turn
-            slow = !(bsum <= 16384.f);
-          } else if (pingpong) {
-            asm volatile("bar.sync %0, 256;" ::"r"(2 + t) : "memory");
-            if (!(t == 1 && j + 1 == nkv)) asm volatile("bar.arrive %0, 256;" ::"r"(3 - t) : "memory");
-          }
-          if (__any_sync(0xffffffffu, slow)) {
-            float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                mx0 = max3(mx0, __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
-                mx1 = max3(mx1, __uint_as_float(sv[c][i + 2]), __uint_as_float(sv[c][i + 3]));
-              }
-            const float mx = fmaxf(mx0, mx1);
-            float alpha = 1.f;
-            if (slow && mx > m_used) {
-              if (m_used != -INFINITY) alpha = ex2((m_used - mx) * SCALE_LOG2);
-              m_used = mx;
-            }
-            if (j > 0) {  // S_t(j) was issued after P_t(j-1) V: that MMA has retired, O_t may be rescaled
-#pragma unroll 1
-              for (int c = 0; c < 4; ++c) {
-                uint32_t o16[16];
-                tmem_ld16(to + c * 16, o16);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o16[i] = __float_as_uint(__uint_as_float(o16[i]) * alpha);
-                tmem_st16(to + c * 16, o16);
-              }
-              l *= alpha;
-            }
-            bsum = exp_block(m_used);  // lanes whose reference did not move reproduce their block bit for bit
-          }
-          l += bsum;
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&p_full[t]);
-        }
-        mbar_wait_sleep(&o_final[t], 0, p.dbg, 8, t);
-        tc_fence_after();
-        const float inv = l > 0.f ? 1.f / l : 0.f;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          tmem_ld32(to + c * 32, sv[c]);
-          tmem_ld_wait();
-          if (r < len_q) {
-            uint32_t ph[16], pl[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float a = __uint_as_float(sv[c][2 * i]) * inv, b = __uint_as_float(sv[c][2 * i + 1]) * inv;
-              ph[i] = pack_bf16x2(a, b);
-              pl[i] = pack_bf16x2_lo(a, b, ph[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              reinterpret_cast<uint4*>(p.ctxh + off + c * 32)[i] = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
-              if (p.ctxl)
-                reinterpret_cast<uint4*>(p.ctxl + off + c * 32)[i] = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
-            }
-          }
-        }
+        softmax_tile(p, t, nt, tmem_base + lane_off + t * 64, tmem_base + lane_off + 128 + t * 64, s_full, p_full, o_final, nkv,
+                     len_kv, len_q, r, off);
       }
     } else if (r < len_q) {
       for (int i = 0; i < 8; ++i) {
@@ -378,10 +391,10 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
   AttnParams p;
   p.q_map = c->qm; p.k_map = c->km; p.vt_map = c->vm;
   p.ctxh = b.ctxh; p.ctxl = b.ctxl; p.kv_shift = kv_shift; p.st = st; p.dbg = h->tc.dbg;
-  dim3 grid((st.Lp + 2 * QT - 1) / (2 * QT), LG_HEADS, st.S);
-  p.rows_per_cta = 2 * QT;
   static const bool no_pp = getenv("LG_ATTN_NO_PINGPONG") && atoi(getenv("LG_ATTN_NO_PINGPONG")) != 0;
   p.pingpong = no_pp ? 0 : 1;
+  dim3 grid((st.Lp + 2 * QT - 1) / (2 * QT), LG_HEADS, st.S);
+  p.rows_per_cta = 2 * QT;
   if ((long)grid.x * grid.y * grid.z < 2 * lg_num_sms()) {  // fewer CTAs than resident slots: one query tile per CTA instead
     p.rows_per_cta = QT;
     grid.x = st.Lp / QT;
