@@ -42,6 +42,7 @@ struct TcLinParams {
                                  // 2: third TMA coordinate = partner sequence (similarity sweeps of the assignment)
   float* part; int* part_arg; int part_stride;  // TEPI_LSE: (max, sumexp) pairs; TEPI_ARGMAX: best / arg, [S*Lp, part_stride]
   const float* term;             // TEPI_ARGMAX: logsigmoid(z) - LSE per token, [S, Lp]
+  int reverse;  // walk the tile list from its end: a kernel that reads what the previous kernel wrote LAST finds it in L2
   float* logmat; int mat_m, mat_n;  // TEPI_ARGMAX, optional: materialise the [B, M+1, N+1] log-assignment matrix (core block)
   const float* bias; long bias_sel_stride;
   float scale;
@@ -179,7 +180,7 @@ struct TileWalk {
   // `store` = its epilogue may write
   __device__ bool next(const TcLinParams& p, TileInfo& mine, bool& store) {
     while (cur < end) {
-      const int id = cur;
+      const int id = p.reverse ? end - 1 - cur : cur;
       cur += step;
       if (MC) {
         const int n_tile = id % n_tiles, rtp = id / n_tiles;
@@ -1335,11 +1336,16 @@ int tc_block(LgHandle* h, const TcBuffers& b, const SeqState& st, int layer, int
   const BlockOff& o = blk == 0 ? h->bself : h->bcross;
   const size_t base = h->o_layers + (size_t)layer * h->layer_stride + (blk == 0 ? 0 : h->bself.total);
   const float* bw = h->wpk + base;
+  // Tile order against the 126 MB L2: every kernel of the chain reads what its predecessor wrote, and only the part written
+  // LAST is still resident.  QKV and ffn.0 walk their tile lists backwards, ffn.3 (and the attention grid) forwards: ffn.3
+  // starts on the hidden tiles ffn.0 finished with, the next QKV on the x images ffn.3 finished with, attention on the
+  // q / k / v of the sequences QKV wrote last, ffn.0 on the context of the sequences attention wrote last.
+  static const bool no_rev = getenv("LG_TC_NO_REVERSE") && atoi(getenv("LG_TC_NO_REVERSE")) != 0;
   {  // QKV (+RoPE) / [to_qk | to_v] projection
     Timer t(h, LG_K_LINEAR, stream);
     Timer t2(h, LG_K_QKV, stream);
     TcLinParams p{};
-    p.epi = TEPI_QKV; p.rope = blk == 0; p.scale = 1.f; p.bias = bw + o.bp;
+    p.epi = TEPI_QKV; p.rope = blk == 0; p.scale = 1.f; p.bias = bw + o.bp; p.reverse = no_rev ? 0 : 1;
     p.q = b.q; p.k = b.k; p.vt = b.vt; p.cs = cs;
     LinDesc ld{b.xh, b.xl, LG_DIM, nullptr, nullptr, 0, base + o.wp, blk == 0 ? 3 * LG_DIM : 2 * LG_DIM, 1, 0};
     int r = run_linear(h, st, ld, p, stream);
@@ -1363,6 +1369,7 @@ int tc_block(LgHandle* h, const TcBuffers& b, const SeqState& st, int layer, int
      // lg_handle.h), so the GEMM reads cat([x, ctx]) and `msg` is never formed
     TcLinParams p{};
     p.epi = TEPI_LN_GELU; p.scale = 1.f; p.bias = bw + (no_fold ? o.b1 : o.b1f); p.ln_g = bw + o.g; p.ln_b = bw + o.be;
+    p.reverse = no_rev ? 0 : 1;
     p.out_h = b.hh; p.out_l = b.hl; p.ldb = LG_FFN;
     LinDesc ld{b.xh, b.xl, LG_DIM, no_fold ? b.msgh : b.ctxh, no_fold ? b.msgl : b.ctxl, LG_DIM, base + (no_fold ? o.w1 : o.w1f),
                LG_FFN, 1, 0};
