@@ -14,7 +14,6 @@
 // Warp roles (384 threads = 3 warpgroups): warpgroup 0 = {warp 0 TMA producer, warp 1 TMEM owner + MMA issuer of
 // tile 0, warp 2 MMA issuer of tile 1, 1 idle warp} shrinks its registers (setmaxnreg.dec); warpgroups 1 and 2 are
 // the softmax warpgroups of query tile 0 / 1 (one query row per thread; warp w reads TMEM lanes 32*(w%4)..).
-#include <stdio.h>
 #include <stdlib.h>
 
 #include "lg_handle.h"
@@ -37,7 +36,6 @@ struct AttnParams {
   __nv_bfloat16* ctxh; __nv_bfloat16* ctxl;
   int kv_shift;
   int rows_per_cta;  // 256 (two query tiles per CTA) or 128 (one: small problems that would not fill the SMs)
-  int npairs, n_items;  // persistent kernel: 256-row work items per (sequence, head) and in total
   int pingpong;      // alternate the exponential phases of the CTA's two query tiles (LG_ATTN_NO_PINGPONG=1 switches it off)
   SeqState st;
   unsigned int* dbg;
@@ -110,29 +108,33 @@ __device__ __forceinline__ void softmax_tile(const AttnParams& p, int t, int nt,
                                              uint64_t* p_full, uint64_t* o_final, int nkv, int len_kv, int len_q, int r, long off) {
         float m_used = -INFINITY, l = 0.f;
         uint32_t sv[2][32];
-        // token ring over the CTA's query tiles (named barrier 2 + tile index): tile t takes its exponentials when tile
-        // t-1 has finished its own; the last tile hands the first token to tile 0.  (Measured with FOUR tiles in one
-        // 640-thread CTA per SM, all 512 TMEM columns, one MMA-issuer warp, ring of four: 8.13 ms of attention per step
-        // against 7.40 with two independent two-tile CTAs per SM -- one tile at a time does not keep the MUFU pipe fed,
-        // a single warp per scheduler leaves issue bubbles that a second tile's exponentials fill.)
+        // The two query tiles of the CTA alternate their exponential phases (a token per scheduler, below).  Measured
+        // alternatives on B200 (B = 32, N = 2048, per launch; this kernel: 385 - 390 us):
+        //  * FOUR tiles in one 640-thread CTA per SM with a ring of four tokens: +10 %;
+        //  * a persistent one-CTA-per-SM kernel with DOUBLE-BUFFERED S (S_{j+1} = Q K_{j+1}^T issued under the exponentials of
+        //    block j, so the wait for S disappears from the tile's chain; 2 tiles x (2 x 64 S + 64 O) = 384 TMEM columns):
+        //    448 us with alternating tiles, 479 free-running; with two threads per row (eight softmax warps per tile,
+        //    barrier.red over the warp pair for the lazy-maximum decision) 450 / 490; with mbarrier tokens per
+        //    scheduler 497; degree-3 polynomial exp2 for 1/8 - 4/8 of the elements on top of any of them: no gain.
+        //    A softmax warp spends ~1100 cycles per 64-key block outside its exponentials even when S is ready (barrier
+        //    round trips ~90-200 cycles each, TMEM load, store drain, branches), and only TMEM for two tiles fits with
+        //    double buffering: four resident tiles that wait for their MMAs beat two that do not.
+        //  (tools/micro/micro_exp.cu: the exponential phase alone runs at 9.8 cycles per MUFU with one warp per scheduler and
+        //  8.2 with two -- the 8-cycle MUFU issue rate -- so the phase itself is not what is slow.)
         const bool pingpong = nt > 1 && p.pingpong;
-        // p.pingpong = 1: one token per CTA (named barriers 2 / 3, 256 threads).  2: one token per SCHEDULER (the warp of
-        // tile 0 and the warp of tile 1 that share a row quarter share the scheduler's MUFU: named barriers 2 + 2 q + t,
-        // 64 threads) -- the hand-over no longer waits for the slowest of four schedulers.  3: as 2, and the token is
-        // passed after the first half of the block's exponentials, so the next warp's scale-and-shift preamble and its
-        // first MUFUs overlap the drain of this one's.
-        const bool per_sched = p.pingpong >= 2, early = p.pingpong == 3;
+        // One token per SCHEDULER: the warp of tile 0 and the warp of tile 1 that own the same row quarter share a
+        // scheduler and its MUFU; named barrier 2 + 2 q + t (64 threads) hands the exponential phase from one to the other,
+        // so a hand-over never waits for the slowest of the four schedulers (a CTA-wide token, barriers 2 / 3 with 256
+        // threads, measured 1 % slower; passing the token after half of the block's exponentials measured the same).
         const int qd = (threadIdx.x / 32) % 4;
-        const int bar_self = per_sched ? 2 + 2 * qd + t : 2 + t;
-        const int bar_next = per_sched ? 2 + 2 * qd + (t ^ 1) : 2 + (t + 1 == nt ? 0 : t + 1);
-        const int bar_cnt = per_sched ? 64 : 256;
+        const int bar_self = 2 + 2 * qd + t, bar_next = 2 + 2 * qd + (t ^ 1);
         const bool ring_last = t + 1 == nt;
-        if (pingpong && ring_last) asm volatile("bar.arrive %0, %1;" ::"r"(bar_next), "r"(bar_cnt) : "memory");  // tile 0 goes first
+        if (pingpong && ring_last) asm volatile("bar.arrive %0, 64;" ::"r"(bar_next) : "memory");  // tile 0 goes first
         // P = exp2(c s - c m_used) of one 64-key block: scale-and-shift and row sum as packed f32x2 operations, P stored
         // in place over S; returns the row sum of the block.  (A degree-3 Cody-Waite polynomial for 12 - 50 % of the
         // exponentials on the FMA pipe, packed f32x2, was measured on B200: 405 - 468 us per launch against 412 with
         // every exponential on the MUFU -- no gain.)
-        auto exp_block = [&](float m, bool pass_early = false) -> float {
+        auto exp_block = [&](float m) -> float {
           const uint64_t sc2 = pack2(SCALE_LOG2, SCALE_LOG2);
           const float nmc = -m * SCALE_LOG2;
           const uint64_t nm2 = pack2(nmc, nmc);
@@ -151,7 +153,6 @@ __device__ __forceinline__ void softmax_tile(const AttnParams& p, int t, int nt,
               pk[i] = *reinterpret_cast<const uint32_t*>(&hh);
             }
             tmem_st16(ts + c * 16, pk);
-            if (c == 0 && pass_early) asm volatile("bar.arrive %0, %1;" ::"r"(bar_next), "r"(bar_cnt) : "memory");
           }
           float a0, a1;
           unpack2(add2(la, lb), a0, a1);
@@ -182,14 +183,13 @@ __device__ __forceinline__ void softmax_tile(const AttnParams& p, int t, int nt,
           float bsum = 0.f;
           bool slow = j == 0;
           if (j > 0) {
-            const bool pass = pingpong && !(ring_last && j + 1 == nkv);
-            if (pingpong) asm volatile("bar.sync %0, %1;" ::"r"(bar_self), "r"(bar_cnt) : "memory");
-            bsum = exp_block(m_used, pass && early);
-            if (pass && !early) asm volatile("bar.arrive %0, %1;" ::"r"(bar_next), "r"(bar_cnt) : "memory");  // the other tile's turn
+            if (pingpong) asm volatile("bar.sync %0, 64;" ::"r"(bar_self) : "memory");
+            bsum = exp_block(m_used);
+            if (pingpong && !(ring_last && j + 1 == nkv)) asm volatile("bar.arrive %0, 64;" ::"r"(bar_next) : "memory");  // the other tile's turn
             slow = !(bsum <= 16384.f);
           } else if (pingpong) {
-            asm volatile("bar.sync %0, %1;" ::"r"(bar_self), "r"(bar_cnt) : "memory");
-            if (!(ring_last && j + 1 == nkv)) asm volatile("bar.arrive %0, %1;" ::"r"(bar_next), "r"(bar_cnt) : "memory");
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_self) : "memory");
+            if (!(ring_last && j + 1 == nkv)) asm volatile("bar.arrive %0, 64;" ::"r"(bar_next) : "memory");
           }
           if (__any_sync(0xffffffffu, slow)) {
             tmem_st_wait();  // the block's first P store must have landed before it is stored again
@@ -380,402 +380,6 @@ __global__ void __launch_bounds__(384, 2) tc_attention2_kernel(const __grid_cons
 }
 
 
-// ------------------------------------------------------------------------------------------------------------------
-// Persistent variant for large problems (at least a few work items per SM): ONE CTA per SM owns all 512 TMEM columns and
-// walks a static list of work items (sequence, head, 256 query rows).  Per query tile: S double-buffered (2 x 64 columns,
-// P in place over the buffer it came from) + O (64 columns):
-//   TMEM map: tile t: S_t[b] at t*128 + b*64 (b = block parity), O_t at 256 + t*64.
-// The MMA warp of a tile issues Q K_{j+2}^T into the buffer P_j V_j has just consumed, so S_{j+1} is complete long before
-// the softmax warpgroup has finished block j: the tile's chain is TMEM load -> exponentials -> P store only (in the
-// two-CTA kernel above the chain also holds P arrival -> MMA warp wake-up -> P V + next Q K^T -> commit, ~600 of ~2900
-// cycles per block).  Work items follow each other without draining: Q is double-buffered in shared memory, the K/V ring
-// and every barrier phase run on across items, the O normalisation + store of one item overlaps the first MMAs of the
-// next.  Barrier phases are tracked with running counters (kv: blocks loaded so far, g: blocks of this tile, c: items of
-// this tile, qit: items), identical in every role because every role skips the same items.
-constexpr int C_KV_STAGES = 6;
-constexpr int C_Q_BYTES = 2 * Q_TILE_BYTES;  // both query tiles of an item
-
-struct ItemInfo {
-  int s, h, r0, len_q, skv, len_kv, nkv, nt;
-  bool active;
-};
-__device__ __forceinline__ ItemInfo decode_item(const AttnParams& p, int w) {
-  ItemInfo it;
-  const int rp = w % p.npairs, sh = w / p.npairs;
-  it.s = sh / LG_HEADS; it.h = sh % LG_HEADS; it.r0 = rp * 2 * QT;
-  it.len_q = p.st.len[it.s];
-  it.active = it.r0 < it.len_q && !lg_pair_stopped(p.st, it.s);
-  it.skv = (it.s + p.kv_shift) % p.st.S;
-  it.len_kv = p.st.len[it.skv];
-  it.nkv = (it.len_kv + KB - 1) / KB;
-  it.nt = (it.len_q - it.r0 > QT) ? 2 : 1;
-  return it;
-}
-
-// exp2 on the FMA / ALU pipes for a packed pair (Cody-Waite: x = n + f, n = floor(x) through a round-down add of
-// 1.5 * 2^23, 2^f by a degree-3 minimax polynomial on [0, 1), relative error 7.6e-5 -- a third of the fp16 rounding of P --
-// and n added into the exponent field).  The MUFU evaluates 16 exponentials per clock and SM, half of what the tile
-// needs to keep up with the tensor core at head dimension 64; every pair taken here frees 16 MUFU cycles of a scheduler
-// for 10 issue slots.  x <= 14.x by construction (the caller's reference maximum is at most 2^14 low), clamped below.
-__device__ __forceinline__ uint64_t add2_rm(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ void exp2_poly_x2(uint64_t x2, float& e0, float& e1) {
-  float x0, x1;
-  unpack2(x2, x0, x1);
-  x0 = fmaxf(x0, -120.f);
-  x1 = fmaxf(x1, -120.f);
-  const uint64_t xc = pack2(x0, x1);
-  const uint64_t magic = pack2(12582912.f, 12582912.f), nmagic = pack2(-12582912.f, -12582912.f);
-  const uint64_t xi = add2_rm(xc, magic);            // 1.5 * 2^23 + floor(x): n sits in the low mantissa bits
-  const uint64_t xf = add2(xi, nmagic);              // floor(x), exact
-  const uint64_t none = pack2(-1.f, -1.f);
-  const uint64_t f = fma2(xf, none, xc);             // x - floor(x) in [0, 1), exact
-  uint64_t pq = fma2(pack2(0.07807237654924393f, 0.07807237654924393f), f, pack2(0.2259994000196457f, 0.2259994000196457f));
-  pq = fma2(pq, f, pack2(0.6958566308021545f, 0.6958566308021545f));
-  pq = fma2(pq, f, pack2(0.9999241232872009f, 0.9999241232872009f));
-  float p0, p1, i0, i1;
-  unpack2(pq, p0, p1);
-  unpack2(xi, i0, i1);
-  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(i0) << 23));
-  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(i1) << 23));
-}
-
-// P = exp2(c s - c m) of 32 keys held in sv, stored as 16 fp16 pairs at tdst; POLY of every 8 pairs take the polynomial
-template <int POLY>
-__device__ __forceinline__ void exp_half(const uint32_t (&sv)[32], uint32_t tdst, uint64_t sc2, uint64_t nm2, uint64_t& la, uint64_t& lb) {
-  uint32_t pk[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const uint64_t x2 = fma2(pack2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sc2, nm2);
-    float e0, e1;
-    if ((((i % 8) + 1) * POLY) / 8 != ((i % 8) * POLY) / 8) {  // POLY pairs spread evenly over every 8
-      exp2_poly_x2(x2, e0, e1);
-    } else {
-      float x0, x1;
-      unpack2(x2, x0, x1);
-      e0 = ex2(x0); e1 = ex2(x1);
-    }
-    if (i & 1) lb = add2(lb, pack2(e0, e1));
-    else la = add2(la, pack2(e0, e1));
-    const __half2 hh = __floats2half2_rn(e0, e1);
-    pk[i] = *reinterpret_cast<const uint32_t*>(&hh);
-  }
-  tmem_st16(tdst, pk);
-}
-// 64-thread named barrier of a warp pair that also ORs a predicate over the pair (barrier.red)
-__device__ __forceinline__ bool pair_any(int bar_id, bool pred) {
-  uint32_t r;
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.u32 q, %2, 0;\n\t"
-      "barrier.cta.red.or.pred p, %1, 64, q;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(r)
-      : "r"(bar_id), "r"((uint32_t)pred)
-      : "memory");
-  return r != 0;
-}
-
-// Threads: warpgroup 0 = {TMA producer, MMA issuer of tile 0, MMA issuer of tile 1, idle}; warpgroups 1-2 = query tile 0,
-// warpgroups 3-4 = query tile 1.  TWO threads per query row: warpgroup `half` of a tile owns keys [32 half, 32 half + 32) of
-// every block, so the two warps of a row quarter (warps q and q + 4 of the tile: the same scheduler, the same TMEM lanes)
-// issue their exponentials together -- one warp alone does not keep its scheduler's MUFU busy (measured: 885 cycles for the
-// 512 MUFU cycles of a tile's block), two do.  The pair shares one reference maximum per row: after the block's
-// exponentials a 64-thread barrier.red ORs "some row sum left the safe range" over the pair, and only then the row maxima
-// and flags are exchanged through shared memory, O / l are rescaled (each thread its 32 columns of O) and the block is redone.
-template <int POLY, int TRACE>
-__global__ void __launch_bounds__(640, 1) tc_attention3_kernel(const __grid_constant__ AttnParams p) {
-  pdl_launch_dependents();
-  pdl_wait();
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(smem_raw)) & 1023u)) & 1023u);
-  uint8_t* sq = smem;                                  // 2 buffers x (2 x 16 KB)
-  uint8_t* skvb = smem + 2 * C_Q_BYTES;                // C_KV_STAGES x 16 KB
-  float2* xch = reinterpret_cast<float2*>(skvb + C_KV_STAGES * B_STAGE_BYTES);  // [2 tiles][128 rows][2 halves] (row maximum, flag)
-  float* xl = reinterpret_cast<float*>(xch + 2 * QT * 2);                        // [2 tiles][128 rows][2 halves] denominators
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xl + 2 * QT * 2);
-  uint64_t* q_full = bars;                        // [2]
-  uint64_t* q_empty = q_full + 2;                 // [2]
-  uint64_t* kv_full = q_empty + 2;                // [C_KV_STAGES]
-  uint64_t* kv_empty = kv_full + C_KV_STAGES;     // [C_KV_STAGES]
-  uint64_t* s_full = kv_empty + C_KV_STAGES;      // [2 tiles][2 buffers]
-  uint64_t* p_full = s_full + 4;                  // [2 tiles][2 buffers] (one per S buffer: the softmax warps may be two blocks ahead of the MMA warp's wait)
-  uint64_t* pv_done = p_full + 4;                 // [2]
-  uint64_t* o_final = pv_done + 2;                // [2]
-  uint64_t* tok = o_final + 2;                    // [4 row quarters][2 tiles]: "the exponentials of tile t may start" on this scheduler
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 8);
-
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.q_map);
-    tma_prefetch_desc(&p.k_map);
-    tma_prefetch_desc(&p.vt_map);
-    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 2); }
-    for (int i = 0; i < C_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); }
-    for (int t = 0; t < 2; ++t) { mbar_init(&pv_done[t], 1); mbar_init(&o_final[t], 1); }
-    for (int i = 0; i < 8; ++i) mbar_init(&tok[i], 2);  // lane 0 of the two warps of the other tile's pair
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0) {
-      if (elect_one()) {
-        uint32_t kv = 0, qit = 0;
-        for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
-          const ItemInfo it = decode_item(p, w);
-          if (!it.active || it.nkv == 0) continue;
-          const uint32_t qb = qit & 1;
-          mbar_wait_sleep(&q_empty[qb], ((qit >> 1) & 1) ^ 1, p.dbg, 9, w);
-          mbar_arrive_expect_tx(&q_full[qb], C_Q_BYTES);
-          tma_load_3d(sq + qb * C_Q_BYTES, &p.q_map, 0, it.r0, it.s * LG_HEADS + it.h, &q_full[qb]);
-          tma_load_3d(sq + qb * C_Q_BYTES + Q_TILE_BYTES, &p.q_map, 0, it.r0 + QT, it.s * LG_HEADS + it.h, &q_full[qb]);
-          for (int j = 0; j < it.nkv; ++j, ++kv) {
-            const uint32_t stage = kv % C_KV_STAGES, round = kv / C_KV_STAGES;
-            mbar_wait_sleep(&kv_empty[stage], (round & 1) ^ 1, p.dbg, 1, j);
-            uint8_t* dst = skvb + stage * B_STAGE_BYTES;
-            mbar_arrive_expect_tx(&kv_full[stage], B_STAGE_BYTES);
-            tma_load_3d(dst, &p.k_map, 0, j * KB, it.skv * LG_HEADS + it.h, &kv_full[stage]);
-            tma_load_3d(dst + K_TILE_BYTES, &p.vt_map, j * KB, 0, it.skv * LG_HEADS + it.h, &kv_full[stage]);
-          }
-          ++qit;
-        }
-      }
-    } else if (warp < 3) {
-      // MMA issuer of tile t.  Per item: S(0), S(1); then per block j: wait P(j) -> O += P(j) V_j -> S(j+2) = Q K_{j+2}^T
-      // into the buffer P(j) lived in (in-order tensor pipe: it is overwritten only after P(j) V_j has consumed it).
-      const int t = warp - 1;
-      constexpr uint32_t idesc = make_idesc(QT, KB, false);  // M=128 N=64, fp16 (both products)
-      const uint64_t kdesc0 = make_sdesc_sw128(smem_u32(skvb));
-      const uint64_t vdesc0 = make_sdesc_sw128(smem_u32(skvb + K_TILE_BYTES));
-      const uint32_t ts0 = tmem_base + t * 128;
-      const uint32_t to_addr = tmem_base + 256 + t * 64;
-      uint32_t kv = 0, qit = 0, g = 0;
-      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
-        const ItemInfo it = decode_item(p, w);
-        if (!it.active || it.nkv == 0) continue;
-        if (t < it.nt) {
-          const uint32_t qb = qit & 1;
-          const uint64_t qdesc = make_sdesc_sw128(smem_u32(sq + qb * C_Q_BYTES + t * Q_TILE_BYTES));
-          const int ncommit = it.nt == 1 ? 2 : 1;  // a lone tile also arrives for the absent one
-          auto issue_qk = [&](int j) {
-            const uint32_t kk = kv + j, stage = kk % C_KV_STAGES;
-            mbar_wait_sleep(&kv_full[stage], (kk / C_KV_STAGES) & 1, p.dbg, 4, j);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t kdesc = kdesc0 + (uint64_t)(stage * (B_STAGE_BYTES >> 4));
-              const uint32_t b = (g + j) & 1;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) mma_ss(ts0 + b * 64, qdesc + 2 * k, kdesc + 2 * k, idesc, k > 0 ? 1u : 0u);
-              mma_commit(&s_full[t * 2 + b]);
-              if (j + 1 == it.nkv)
-                for (int i = 0; i < ncommit; ++i) mma_commit(&q_empty[qb]);  // Q of this item is no longer needed
-            }
-            __syncwarp();
-          };
-          mbar_wait_sleep(&q_full[qb], (qit >> 1) & 1, p.dbg, 2, w);
-          issue_qk(0);
-          if (it.nkv > 1) issue_qk(1);
-          for (int j = 0; j < it.nkv; ++j) {
-            const uint32_t gg = g + j, stage = (kv + j) % C_KV_STAGES;
-            mbar_wait_sleep(&p_full[t * 2 + (gg & 1)], (gg >> 1) & 1, p.dbg, 5, j * 2 + t);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t vdesc = vdesc0 + (uint64_t)(stage * (B_STAGE_BYTES >> 4));
-              const uint32_t tp = ts0 + (gg & 1) * 64;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) mma_ts(to_addr, tp + ks * 8, vdesc + 2 * ks, idesc, (j > 0 || ks > 0) ? 1u : 0u);
-              for (int i = 0; i < ncommit; ++i) mma_commit(&kv_empty[stage]);
-              mma_commit(&pv_done[t]);
-              if (j + 1 == it.nkv) mma_commit(&o_final[t]);
-            }
-            __syncwarp();
-            if (j + 2 < it.nkv) issue_qk(j + 2);
-          }
-          g += it.nkv;
-        }
-        kv += it.nkv;
-        ++qit;
-      }
-    }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    const int t = (warp - 4) / 8;          // query tile
-    const int hf = ((warp - 4) / 4) & 1;   // which 32 keys of every block
-    const int quarter = warp % 4;
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t ts0 = tmem_base + lane_off + t * 128;
-    const uint32_t to = tmem_base + lane_off + 256 + t * 64 + hf * 32;   // this thread's 32 columns of O_t
-    const int pair_bar = 4 + t * 4 + quarter;                            // named barriers 4..11: one per warp pair
-    float2* xme = xch + (t * QT + row) * 2 + hf;
-    const float2* xother = xch + (t * QT + row) * 2 + (hf ^ 1);
-    float* lme = xl + (t * QT + row) * 2 + hf;
-    const float* lother = xl + (t * QT + row) * 2 + (hf ^ 1);
-    uint32_t g = 0, c = 0, tkn = 0;
-    uint32_t sv[32];
-    for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
-      const ItemInfo it = decode_item(p, w);
-      if (!it.active) continue;
-      const int r = it.r0 + t * QT + row;
-      const long off = ((long)it.s * p.st.Lp + r) * LG_DIM + it.h * LG_HDIM + hf * 32;
-      if (it.nkv == 0) {
-        if (r < it.len_q)
-          for (int i = 0; i < 4; ++i) {
-            reinterpret_cast<uint4*>(p.ctxh + off)[i] = make_uint4(0, 0, 0, 0);
-            if (p.ctxl) reinterpret_cast<uint4*>(p.ctxl + off)[i] = make_uint4(0, 0, 0, 0);
-          }
-        continue;
-      }
-      if (t >= it.nt) continue;
-      const int nkv = it.nkv;
-      float m_used = -INFINITY, l = 0.f;
-      // Token between the item's two query tiles, PER SCHEDULER (mbarriers tok[quarter][tile], two arrivals: lane 0 of
-      // both warps of the other tile's pair): the exponentials of the two warp pairs that share a scheduler's MUFU
-      // alternate, so one pair's TMEM loads / stores / barrier traffic run under the other's exponentials (free-running
-      // pairs fall into lockstep: both in their exponentials, then both outside).  Tile 1 hands tile 0 the first token.
-      const bool pingpong = it.nt > 1 && p.pingpong;
-      uint64_t* tok_self = &tok[quarter * 2 + t];
-      uint64_t* tok_next = &tok[quarter * 2 + (t ^ 1)];
-      auto token_pass = [&]() {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tok_next);
-      };
-      auto token_wait = [&]() {
-        mbar_wait_sleep(tok_self, tkn & 1, p.dbg, 10, t);
-        ++tkn;
-      };
-      if (pingpong && t == 1) token_pass();
-      const uint64_t sc2 = pack2(SCALE_LOG2, SCALE_LOG2);
-      for (int j = 0; j < nkv; ++j) {
-        const uint32_t gg = g + j, b = gg & 1;
-        const uint32_t ts = ts0 + b * 64;
-        long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0, tr4 = 0;
-        const bool tracing = TRACE && blockIdx.x == 0 && w == blockIdx.x && lane == 0 && quarter == 0 && hf == 0 && j >= 8 && j < 24;
-        if (TRACE) tr0 = clock64();
-        mbar_wait_sleep(&s_full[t * 2 + b], (gg >> 1) & 1, p.dbg, 6, j * 2 + t);
-        tc_fence_after();
-        if (TRACE) tr1 = clock64();
-        const int valid = it.len_kv - j * KB - hf * 32;  // live keys among this thread's 32
-        tmem_ld32(ts + hf * 32, sv);
-        tmem_ld_wait();
-        if (valid < 32) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i >= valid) sv[i] = 0xff800000u;
-        }
-        float bsum = 0.f;
-        bool slow = j == 0;
-        if (j > 0) {
-          if (TRACE) tr2 = clock64();
-          if (pingpong) token_wait();
-          if (TRACE) tr3 = clock64();
-          const float nmc = -m_used * SCALE_LOG2;
-          uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
-          exp_half<POLY>(sv, ts + hf * 16, sc2, pack2(nmc, nmc), la, lb);
-          float a0, a1;
-          unpack2(add2(la, lb), a0, a1);
-          bsum = a0 + a1;
-          if (TRACE) tr4 = clock64();
-          if (pingpong && !(t == 1 && j + 1 == nkv)) token_pass();
-          slow = !(bsum <= 8192.f);   // every P of this half <= 2^13
-        } else if (pingpong) {
-          token_wait();
-          if (!(t == 1 && j + 1 == nkv)) token_pass();
-        }
-        if (pair_any(pair_bar, slow)) {
-          // rare after the first block: exchange (row maximum of the half, flag) with the partner thread of the row
-          tmem_st_wait();  // the block's first P store must have landed before it is stored again
-          float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            mx0 = max3(mx0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
-            mx1 = max3(mx1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
-          }
-          *xme = make_float2(fmaxf(mx0, mx1), slow ? 1.f : 0.f);
-          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-          const float2 o = *xother;
-          const float mx = fmaxf(fmaxf(mx0, mx1), o.x);
-          const bool row_slow = slow || o.y != 0.f;
-          float alpha = 1.f;
-          if (row_slow && mx > m_used) {
-            if (m_used != -INFINITY) alpha = ex2((m_used - mx) * SCALE_LOG2);
-            m_used = mx;
-          }
-          if (j > 0) {  // O_t may be rescaled once P(j-1) V has retired (P(j) V cannot be issued before this block arrives)
-            mbar_wait_sleep(&pv_done[t], (gg - 1) & 1, p.dbg, 7, j * 2 + t);
-            tc_fence_after();
-#pragma unroll 1
-            for (int cc = 0; cc < 2; ++cc) {
-              uint32_t o16[16];
-              tmem_ld16(to + cc * 16, o16);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o16[i] = __float_as_uint(__uint_as_float(o16[i]) * alpha);
-              tmem_st16(to + cc * 16, o16);
-            }
-            l *= alpha;
-          }
-          const float nmc = -m_used * SCALE_LOG2;
-          uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
-          exp_half<0>(sv, ts + hf * 16, sc2, pack2(nmc, nmc), la, lb);  // the redone block takes every exponential on the MUFU
-          float a0, a1;
-          unpack2(add2(la, lb), a0, a1);
-          bsum = a0 + a1;
-        }
-        l += bsum;
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[t * 2 + b]);
-        if (TRACE && tracing)
-          printf("trace tile %d block %2d: top %lld | wait S %4lld | ld %4lld | token %4lld | exp %4lld | tail %4lld\n", t, j, tr0,
-                 tr1 - tr0, tr2 - tr1, tr3 - tr2, tr4 - tr3, clock64() - tr4);
-      }
-      g += nkv;
-      // denominators of the two halves (own slots: a slow last block may still be reading the maxima)
-      *lme = l;
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      l += *lother;
-      mbar_wait_sleep(&o_final[t], c & 1, p.dbg, 8, t);
-      ++c;
-      tc_fence_after();
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      tmem_ld32(to, sv);
-      tmem_ld_wait();
-      if (r < it.len_q) {
-        uint32_t ph[16], pl[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float a = __uint_as_float(sv[2 * i]) * inv, bq = __uint_as_float(sv[2 * i + 1]) * inv;
-          ph[i] = pack_bf16x2(a, bq);
-          pl[i] = pack_bf16x2_lo(a, bq, ph[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          reinterpret_cast<uint4*>(p.ctxh + off)[i] = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
-          if (p.ctxl) reinterpret_cast<uint4*>(p.ctxl + off)[i] = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
-        }
-      }
-      // O_t is rewritten by P(0) V of the tile's next item, issued only after this thread's next p_full arrival; the
-      // exchange slots are rewritten only after further pair barriers
-      tc_fence_before();
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
-}
-
-constexpr int ATTN3_DEFAULT_VAR = 0;
 struct AttnMapCache {
   const void* q; const void* k; const void* vt; int S, Lp;
   CUtensorMap qm, km, vm;
@@ -803,44 +407,9 @@ int tc_attention(LgHandle* h, const TcBuffers& b, const SeqState& st, int kv_shi
   p.q_map = c->qm; p.k_map = c->km; p.vt_map = c->vm;
   p.ctxh = b.ctxh; p.ctxl = b.ctxl; p.kv_shift = kv_shift; p.st = st; p.dbg = h->tc.dbg;
   const char* npp = getenv("LG_ATTN_NO_PINGPONG");
-  const char* ppm = getenv("LG_ATTN_PP");  // 1 per CTA, 2 per scheduler, 3 per scheduler + early pass
-  p.pingpong = (npp && atoi(npp) != 0) ? 0 : (ppm ? atoi(ppm) : 1);
+  p.pingpong = (npp && atoi(npp) != 0) ? 0 : 1;
   dim3 grid((st.Lp + 2 * QT - 1) / (2 * QT), LG_HEADS, st.S);
   p.rows_per_cta = 2 * QT;
-  p.npairs = (int)grid.x;
-  p.n_items = (int)(grid.x * grid.y * grid.z);
-  // large problems: the persistent one-CTA-per-SM kernel with double-buffered S (LG_ATTN_V=2 / 3 forces a variant)
-  const char* ev = getenv("LG_ATTN_V");
-  const int force = ev ? atoi(ev) : 0;
-  if (force == 3 || (force != 2 && p.n_items >= 3 * lg_num_sms())) {
-    constexpr int smem3 = 2 * C_Q_BYTES + C_KV_STAGES * B_STAGE_BYTES + 2 * QT * 2 * 12 + 1024 + 1024;
-    // LG_ATTN3_VAR = POLY: pairs of every 8 whose exponentials take the polynomial (measurement aid)
-    const char* vv = getenv("LG_ATTN3_VAR");
-    const int var = vv ? atoi(vv) : ATTN3_DEFAULT_VAR;
-    void (*kern)(const AttnParams) = nullptr;
-    switch (var) {
-      case 0: kern = tc_attention3_kernel<0, 0>; break;
-      case 1: kern = tc_attention3_kernel<1, 0>; break;
-      case 2: kern = tc_attention3_kernel<2, 0>; break;
-      case 3: kern = tc_attention3_kernel<3, 0>; break;
-      case 100: kern = tc_attention3_kernel<0, 1>; break;  // + clock trace of one warp (printf)
-      case 102: kern = tc_attention3_kernel<2, 1>; break;
-      default: return lg_set_error("LG_ATTN3_VAR: no such variant");
-    }
-    if (int r = lg_func_smem_once((const void*)kern, smem3)) return r;
-    cudaLaunchConfig_t cfg{};
-    cudaLaunchAttribute at[1];
-    cfg.gridDim = dim3(p.n_items < lg_num_sms() ? p.n_items : lg_num_sms()); cfg.blockDim = dim3(640);
-    cfg.dynamicSmemBytes = smem3; cfg.stream = stream;
-    if (tc_use_pdl()) {
-      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      at[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-    }
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
-    if (e != cudaSuccess) return lg_set_cuda_error(e, __FILE__, __LINE__);
-    return 0;
-  }
   if ((long)grid.x * grid.y * grid.z < 2 * lg_num_sms()) {  // fewer CTAs than resident slots: one query tile per CTA instead
     p.rows_per_cta = QT;
     grid.x = st.Lp / QT;
