@@ -260,10 +260,13 @@ class LightGlue(nn.Module):
         matches -1 / scores 0 / prune 0; every pair's result equals its own B=1 call.
 
         Deviation from the reference for B > 1 with adaptive depth / width ON: early exit and point pruning are
-        decided PER PAIR on the device, and ``stop`` is the maximum over the batch.  The reference takes one
+        decided PER PAIR on the device, ``stop`` is the maximum over the batch and ``stops`` (extra key for B > 1) lists
+        every pair's exit layer.  The reference takes one
         batch-global decision (the low-confidence count is summed over the batch and divided by one pair's m + n,
         645-656; ``torch.where(mask)[1]`` concatenates the columns of all rows, 554/562), which is only well defined
-        for B == 1 -- there the results are identical (fixtures ``adaptive_*``).  With pruning / early exit off
+        for B == 1 -- there the results are identical (fixtures ``adaptive_*``); in a batch of two COPIES of one pair the
+        reference runs all nine layers where the pair alone stops after six (tests/test_reference_batch_semantics.py
+        runs the unmodified reference file to show it).  With pruning / early exit off
         (``depth_confidence = width_confidence = -1``) batched and single calls agree bit for bit.
         """
         for key in self.required_data_keys:
@@ -417,7 +420,7 @@ class LightGlue(nn.Module):
             "prune0": prune0,
             "prune1": prune1,
         }
-        if ragged:  # ragged batch: per-pair exit layers for split_outputs
+        if ragged or b > 1:  # per-pair exit layers (split_outputs of a ragged batch; a dense batch decides per pair too)
             res["stops"] = [int(v) for v in meta_h[0].tolist()]
         return res
 

@@ -213,6 +213,26 @@ def test_per_layer_residual_stream_against_oracle(prec, tol):
     print(f"[{prec}] per-layer max relative deviation {worst:.2e}")
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_batched_early_exit_is_decided_per_pair(prec):
+    """The documented deviation for B > 1 (tests/test_reference_batch_semantics.py shows what the reference does instead):
+    in one batch {pair 41, pair 41 again, pair 42} every pair exits where it exits alone -- the oracle's B = 1 result --
+    and returns its own B = 1 matches; ``stop`` is the maximum, ``stops`` the per-pair list."""
+    sd = synth.make_state_dict(adaptive=True, seed=2)
+    pairs = [synth.make_pair(192, b=1, seed=s)[0] for s in (41, 41, 42)]
+    refs = [oracle.forward(sd, p, depth_confidence=0.95, width_confidence=-1) for p in pairs]
+    assert [int(r["stop"]) for r in refs] == [6, 6, 9]
+    m = LightGlue(features=None, precision=prec, depth_confidence=0.95, width_confidence=-1)
+    m.load_state_dict(sd, strict=False)
+    m = m.cuda()
+    batch = {k: {kk: torch.cat([p[k][kk] for p in pairs]) for kk in pairs[0][k]} for k in ("image0", "image1")}
+    out = m(to_cuda(batch))
+    assert out["stops"] == [6, 6, 9] and int(out["stop"]) == 9
+    for i, r in enumerate(refs):
+        assert torch.equal(out["matches0"][i].cpu(), r["matches0"][0]) and torch.equal(out["matches1"][i].cpu(), r["matches1"][0])
+        assert float((out["matching_scores0"][i].cpu() - r["matching_scores0"][0]).abs().max()) < 1e-3
+
+
 def test_pruned_to_zero_points_ends_the_pair_like_the_reference():
     """Pruning that leaves an image without points: the reference breaks at the top of the next layer and answers from
     its empty branch (lightglue.py:539-540, 568-588): nothing matched, stop = that layer + 1."""
