@@ -52,7 +52,7 @@ LG_API int sp_destroy(SpHandle* h);
 LG_API int64_t sp_max_keypoints(const SpHandle* h, int32_t H, int32_t W);
 LG_API size_t sp_workspace_bytes(const SpHandle* h, int32_t B, int32_t H, int32_t W);
 
-/* Replaces SuperPoint.forward (163-227) for a grayscale batch image [B, 1, H, W] fp32 (H, W multiples of 8).
+/* Replaces SuperPoint.forward (163-227) for a grayscale batch image [B, 1, H, W] fp32 (any H, W >= 8: the poolings floor as in the reference).
  * keypoints [B, cap, 2] (x, y) fp32, scores [B, cap], descriptors [B, cap, 256] (unit norm), counts [B]:
  * the first counts[b] rows of image b are valid -- in the reference's order (row-major, or by descending score
  * when top-k applies) -- the rest is zero. */

@@ -85,7 +85,7 @@ extern "C" int sp_forward(SpHandle* h, const float* image, int32_t B, int32_t H,
                           float* scores, float* descriptors, int32_t* counts, void* workspace, size_t workspace_bytes,
                           void* stream_) {
   if (!h || !image || !keypoints || !scores || !descriptors || !counts) return lg_set_error("sp_forward: null argument");
-  if (B <= 0 || H < 8 || W < 8 || H % SP_CELL || W % SP_CELL) return lg_set_error("sp_forward: H and W must be multiples of 8");
+  if (B <= 0 || H < SP_CELL || W < SP_CELL) return lg_set_error("sp_forward: H and W must be at least 8");
   if (cap < max_keypoints(h->cfg, H, W)) return lg_set_error("sp_forward: output capacity below sp_max_keypoints()");
   SpWorkspace w;
   sp_carve((char*)workspace, B, H, W, cap, &w);
@@ -97,7 +97,8 @@ extern "C" int sp_forward(SpHandle* h, const float* image, int32_t B, int32_t H,
   int rc;
   if (h->tc) {  // convolutions on the tensor cores, then the shared post-processing functors
     rc = sp_tc_backbone(h->tc, h->wts, image, B, H, W, (char*)workspace + w.bytes, w.logits, w.dense, stream);
-    if (!rc) rc = sp_run_post(ex, prm, B, H, W, cap, w, keypoints, scores, descriptors, SpCudaStages{stream});
+    if (!rc) rc = sp_run_post(ex, prm, B, H / SP_CELL * SP_CELL, W / SP_CELL * SP_CELL, cap, w, keypoints, scores, descriptors,
+                              SpCudaStages{stream});
   } else {
     rc = sp_run(ex, h->wts, prm, image, B, H, W, cap, w, keypoints, scores, descriptors);
   }

@@ -307,7 +307,9 @@ inline void sp_carve(char* base, int B, int H, int W, long out_cap, SpWorkspace*
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// the forward: SuperPoint.forward (163-227) on a grayscale batch [B,1,H,W], H and W multiples of 8.
+// the forward: SuperPoint.forward (163-227) on a grayscale batch [B,1,H,W], H, W >= 8 (any size: the three poolings floor,
+// 173-179, so the heads see Hc = H / 8, Wc = W / 8 cells and the score map covers the top-left 8 Hc x 8 Wc pixels, 188-190;
+// the rows / columns beyond it still feed the first convolutions' 3x3 neighbourhoods, as in the reference).
 // `exec.run(f)` executes functor f for every index in [0, f.count()); returns non-zero on failure.
 // Outputs: kpts [B,out_cap,2] (x, y), kscores [B,out_cap], desc [B,out_cap,256], counts = ws.n_sel [B].
 // ---------------------------------------------------------------------------------------------------------------
@@ -373,6 +375,7 @@ struct SpFunctorStages {
 };
 
 // Part 2: scores, NMS, keypoint selection, descriptor normalisation + sampling on ws.logits / ws.dense.
+// H, W here are the SCORE MAP's extents (8 Hc, 8 Wc): the image's own, rounded down to multiples of 8.
 template <class Exec, class Stages = SpFunctorStages>
 int sp_run_post(Exec& exec, const SpParams& prm, int B, int H, int W, long out_cap, const SpWorkspace& ws, float* kpts,
                 float* kscores, float* desc, const Stages& stages = Stages()) {
@@ -415,5 +418,5 @@ int sp_run(Exec& exec, const float* wts, const SpParams& prm, const float* image
            const SpWorkspace& ws, float* kpts, float* kscores, float* desc) {
   int rc = sp_run_backbone(exec, wts, image, B, H, W, ws);
   if (rc) return rc;
-  return sp_run_post(exec, prm, B, H, W, out_cap, ws, kpts, kscores, desc);
+  return sp_run_post(exec, prm, B, H / SP_CELL * SP_CELL, W / SP_CELL * SP_CELL, out_cap, ws, kpts, kscores, desc);
 }

@@ -128,8 +128,8 @@ class SuperPoint(nn.Module):
             image = (image * wts).sum(1, keepdim=True)
         b, c, hh, ww = image.shape
         assert c == 1
-        if hh % 8 or ww % 8:
-            raise ValueError(f"image size {ww}x{hh}: this path needs height and width to be multiples of 8")
+        if hh < 8 or ww < 8:
+            raise ValueError(f"image size {ww}x{hh}: height and width must be at least 8 (one detector cell)")
         device = image.device
         image = image.detach().to(torch.float32).contiguous()
         with torch.cuda.device(device):
@@ -163,8 +163,10 @@ class SuperPoint(nn.Module):
 
     @torch.no_grad()
     def extract(self, img: torch.Tensor, **conf) -> dict:
-        """``Extractor.extract`` (utils.py:136-147): add the batch dimension, optionally resize the longer side to
-        ``resize`` (rounded to multiples of 8 here), run ``forward``, map keypoints back to the original pixels."""
+        """``Extractor.extract`` (utils.py:136-147): add the batch dimension, resize the longer side to ``resize``
+        (``ImagePreprocessor``, utils.py:26-38: ``kornia.geometry.transform.resize(side="long", antialias=True)``: the long
+        side becomes ``resize`` and the other ``int(resize / aspect)`` -- truncated, kornia's ``_side_to_image_size``; kornia
+        itself is not a dependency here), run ``forward``, map keypoints back to the original pixels."""
         if img.dim() == 3:
             img = img[None]
         assert img.dim() == 4 and img.shape[0] == 1
@@ -172,9 +174,8 @@ class SuperPoint(nn.Module):
         resize = {**self.preprocess_conf, **conf}.get("resize")
         nh, nw = h, w
         if resize is not None:
-            s = resize / max(h, w)
-            nh, nw = int(round(h * s)), int(round(w * s))
-        nh, nw = max(8, nh // 8 * 8), max(8, nw // 8 * 8)
+            aspect = w / h
+            nh, nw = (int(resize / aspect), int(resize)) if aspect >= 1.0 else (int(resize), int(resize * aspect))
         if (nh, nw) != (h, w):
             img = torch.nn.functional.interpolate(img, size=(nh, nw), mode="bilinear", antialias=True, align_corners=False)
         scales = torch.tensor([nw / w, nh / h], device=img.device, dtype=torch.float32)

@@ -1,6 +1,6 @@
 """Generate tests/golden/sp_*.pt by running the UNMODIFIED reference SuperPoint in this container.
 
-    python oracle/make_golden_superpoint.py       # needs /root/reference (read-only); CPU, fp32
+    python oracle/make_golden_superpoint.py [case ...]   # needs /root/reference (read-only); CPU, fp32
 
 ``lightglue/superpoint.py`` imports ``kornia.color.rgb_to_grayscale`` (absent here) and ``.utils.Extractor`` (which
 imports kornia and cv2), and its constructor downloads ``superpoint_v1.pth``.  Neither is on the path this oracle
@@ -33,6 +33,8 @@ CASES = {
     "sp_480x640_top512": dict(h=480, w=640, b=1, seed=12, conf=dict(max_num_keypoints=512)),
     "sp_b2_top256": dict(h=240, w=320, b=2, seed=13, conf=dict(max_num_keypoints=256)),
     "sp_nms2_thr01": dict(h=160, w=240, b=1, seed=14, conf=dict(nms_radius=2, detection_threshold=0.1, remove_borders=8)),
+    # neither extent a multiple of 8, odd at several pooling levels (203 -> 101 -> 50 -> 25, 317 -> 158 -> 79 -> 39)
+    "sp_odd_203x317": dict(h=203, w=317, b=1, seed=17, conf={}),
 }
 
 
@@ -71,7 +73,10 @@ def main():
     weights = sps.make_superpoint_state_dict(0)
     ref = load_reference(weights)
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])  # optional: names of the cases to (re)generate
     for name, rc in CASES.items():
+        if only and name not in only:
+            continue
         image = sps.make_image(rc["h"], rc["w"], rc["b"], rc["seed"])
         model = ref.SuperPoint(**rc["conf"]).eval()
         if rc["b"] == 1 or rc["conf"].get("max_num_keypoints"):

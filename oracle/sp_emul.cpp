@@ -51,7 +51,7 @@ long sp_emul_max_keypoints(int nms_radius, int max_num_keypoints, int H, int W) 
 // returns 0 on success; outputs as sp_forward (include/superpoint_b200.h)
 int sp_emul_forward(const float* weights, int nms_radius, int max_num_keypoints, int remove_borders, float detection_threshold,
                     const float* image, int B, int H, int W, long cap, float* kpts, float* scores, float* desc, int* counts) {
-  if (H % SP_CELL || W % SP_CELL) return 1;
+  if (H < SP_CELL || W < SP_CELL) return 1;
   SpWorkspace w;
   sp_carve(nullptr, B, H, W, cap, &w);
   char* base = (char*)malloc(w.bytes + 256);

@@ -82,7 +82,7 @@ def forward(
     detection_threshold: float = 0.0005,
     remove_borders: int = 4,
 ) -> Dict[str, List[torch.Tensor]]:
-    """SuperPoint.forward (163-227) on a grayscale batch [B,1,H,W] (H, W multiples of 8).  Returns per-image
+    """SuperPoint.forward (163-227) on a grayscale batch [B,1,H,W] (any H, W >= 8; max_pool2d floors).  Returns per-image
     lists (the reference stacks them, which needs equal counts): keypoints [K,2] (x, y), keypoint_scores [K],
     descriptors [K,256]."""
     feat = encoder(w, image)

@@ -36,6 +36,6 @@ def make_superpoint_state_dict(seed: int = 0, detector_gain: float = 4.0) -> Dic
 def make_image(h: int, w: int, b: int = 1, seed: int = 0) -> torch.Tensor:
     """[b, 1, h, w] in [0, 1]: random 8x8 blocks plus per-pixel noise (exact fp32 arithmetic only)."""
     g = torch.Generator().manual_seed(seed)
-    coarse = torch.rand(b, 1, h // 8, w // 8, generator=g)
+    coarse = torch.rand(b, 1, (h + 7) // 8, (w + 7) // 8, generator=g)  # (extents that are not multiples of 8: cropped blocks)
     fine = torch.rand(b, 1, h, w, generator=g)
-    return coarse.repeat_interleave(8, 2).repeat_interleave(8, 3) * 0.7 + fine * 0.3
+    return coarse.repeat_interleave(8, 2).repeat_interleave(8, 3)[:, :, :h, :w] * 0.7 + fine * 0.3

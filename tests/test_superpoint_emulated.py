@@ -18,7 +18,7 @@ from oracle import superpoint_synth as sps
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CASES = ["sp_240x320", "sp_b2_top256", "sp_nms2_thr01", "sp_480x640_top512"]
+CASES = ["sp_240x320", "sp_b2_top256", "sp_nms2_thr01", "sp_480x640_top512", "sp_odd_203x317"]
 
 
 @pytest.fixture(scope="module")
