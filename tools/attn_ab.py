@@ -1,7 +1,10 @@
-"""A/B of the attention kernel variants through lg_attention: correctness against torch (fp64 softmax on the
-fp16-rounded operands) on a few shapes, then device time per launch at the bench shape.
+"""A/B of attention-kernel switches through lg_attention on one box: correctness against torch (fp64 softmax on the
+fp16-rounded operands) on a few shapes, then device time per launch at the bench shape, once per environment set.
 
-    python tools/attn_ab.py [--variants 2,3] [--env LG_ATTN_NO_PINGPONG=1]"""
+    python tools/attn_ab.py --env-sets "|LG_ATTN_NO_PINGPONG=1"      # default build vs no exponential-phase token
+
+(The logs under profiles/r2_y_attention_*.log were produced by an earlier form of this tool that also selected the
+experimental persistent kernel of commit 8fb04ec: `v2` there is the shipped kernel, `v3:<variant>:<no token>` the others.)"""
 import argparse
 import os
 import sys
@@ -13,13 +16,12 @@ sys.path.insert(0, ROOT)
 from lightglue_b200 import LightGlue  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--variants", default="2,3")
+ap.add_argument("--env-sets", default="", help="'|'-separated sets of ';'-separated NAME=VALUE assignments; '' = none")
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--n", type=int, default=2048)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--precision", default="bf16x3")
 ap.add_argument("--skip-check", action="store_true")
-ap.add_argument("--configs", default="", help="comma list of V:VAR:NOPP:PP (LG_ATTN_V : LG_ATTN3_VAR : LG_ATTN_NO_PINGPONG : LG_ATTN_PP), overrides --variants")
 a = ap.parse_args()
 
 
@@ -29,19 +31,15 @@ def ref(q, k, v):
 
 
 m = LightGlue(features=None, precision=a.precision, depth_confidence=-1, width_confidence=-1).eval().cuda()
-cfg_file = os.path.join(ROOT, "tools", "attn_configs.txt")
-if not a.configs and os.path.exists(cfg_file):
-    a.configs = ",".join(open(cfg_file).read().split())
-cfgs = [c.split(":") for c in a.configs.split(",")] if a.configs else [[v, "", ""] for v in a.variants.split(",")]
-for cfg in cfgs:
-    v = ":".join(cfg)
-    os.environ["LG_ATTN_V"] = cfg[0]
-    for key, val in (("LG_ATTN3_VAR", cfg[1] if len(cfg) > 1 else ""), ("LG_ATTN_NO_PINGPONG", cfg[2] if len(cfg) > 2 else ""),
-                     ("LG_ATTN_PP", cfg[3] if len(cfg) > 3 else "")):
-        if val:
-            os.environ[key] = val
-        else:
-            os.environ.pop(key, None)
+touched = set()
+for env_set in a.env_sets.split("|"):
+    for name in touched:
+        os.environ.pop(name, None)
+    for kv in filter(None, env_set.split(";")):
+        name, val = kv.split("=", 1)
+        os.environ[name] = val
+        touched.add(name)
+    tag = env_set or "default"
     if not a.skip_check:
         for (b, mm, nn) in [(2, 300, 517), (2, 2048, 2048), (2, 64, 1), (3, 1000, 130)]:
             g = torch.Generator(device="cuda").manual_seed(mm * 7 + nn)
@@ -55,8 +53,8 @@ for cfg in cfgs:
                 r1 = ref(q1, k0 if cross else k1, v0 if cross else v1)
                 e0, e1 = float((c0 - r0).abs().max()), float((c1 - r1).abs().max())
                 ok = e0 < 3e-3 and e1 < 3e-3 and bool(torch.isfinite(c0).all()) and bool(torch.isfinite(c1).all())
-                print(f"v{v} check b={b} m={mm} n={nn} cross={cross}: {e0:.2e} {e1:.2e} {'ok' if ok else 'FAIL'} "
-                      f"timeout={m.debug_timeout_code() if hasattr(m, 'debug_timeout_code') else '-'}", flush=True)
+                print(f"[{tag}] check b={b} m={mm} n={nn} cross={cross}: {e0:.2e} {e1:.2e} {'ok' if ok else 'FAIL'} "
+                      f"timeout={m.debug_timeout_code()}", flush=True)
     g = torch.Generator(device="cuda").manual_seed(0)
     mk = lambda s: torch.randn(a.batch, 4, a.n, 64, device="cuda", generator=g) * s  # noqa: E731
     t = [mk(2.0), mk(2.0), mk(1.0), mk(2.0), mk(2.0), mk(1.0)]
@@ -72,5 +70,5 @@ for cfg in cfgs:
         m.timing = False
         us = ms / cnt * 1e3
         flops = 4.0 * a.n * a.n * 64 * 4 * 2 * a.batch
-        print(f"v{v} B={a.batch} N={a.n} cross={cross}: {us:.1f} us/launch, {flops / us / 1e6:.0f} TFLOP/s "
-              f"= {flops / us / 1e6 / 1449.7:.3f}", flush=True)
+        print(f"[{tag}] B={a.batch} N={a.n} cross={cross}: {us:.1f} us/launch, {flops / us / 1e6:.0f} TFLOP/s "
+              f"= {flops / us / 1e6 / 1449.7:.3f} of the sustained bf16 peak", flush=True)
