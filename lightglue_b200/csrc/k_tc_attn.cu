@@ -133,7 +133,8 @@ __device__ __forceinline__ void softmax_tile(const AttnParams& p, int t, int nt,
         // P = exp2(c s - c m_used) of one 64-key block: scale-and-shift and row sum as packed f32x2 operations, P stored
         // in place over S; returns the row sum of the block.  (A degree-3 Cody-Waite polynomial for 12 - 50 % of the
         // exponentials on the FMA pipe, packed f32x2, was measured on B200: 405 - 468 us per launch against 412 with
-        // every exponential on the MUFU -- no gain.)
+        // every exponential on the MUFU -- no gain; measured again with a degree-4 polynomial and the per-scheduler token:
+        // 397 us for 1 pair in 8, 411 for 2 in 8, against 389, profiles/r2_y_attention_poly_exp2.log.)
         auto exp_block = [&](float m) -> float {
           const uint64_t sc2 = pack2(SCALE_LOG2, SCALE_LOG2);
           const float nmc = -m * SCALE_LOG2;
