@@ -205,25 +205,28 @@ class CpuReference:
 
 def run_reference(args, rank: int):
     """--impl reference: the reference's own CPU implementation of the path (the unmodified reference file when
-    oracle/_ref holds it, else the oracle port) on this host's cores.  One step = one N=2048 pair (a bounded sample of
-    the 32-pair batch); the whole run is capped at ~2 minutes."""
+    oracle/_ref holds it, else the oracle port) on this host's cores.  One step = one forward of the calibrated number of
+    N=2048 pairs (a bounded sample of the 32-pair batch); the timed steps are capped at ~100 s in total (`steps` = the steps
+    actually run, `steps_requested` = K)."""
     if rank != 0:
         return
     cpu = CpuReference()
     for _ in range(min(args.warmup, 2)):
         cpu.run(1)
     t_all = time.perf_counter()
-    done, secs = 0, 0.0
+    done, secs, n_steps = 0, 0.0, 0
     for _ in range(args.steps):
         d, dt = cpu.run(1)
         done += d
         secs += dt
+        n_steps += 1
         if time.perf_counter() - t_all > 100:
             break
     value = done / secs
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
-        "steps": done, "warmup": min(args.warmup, 2), "ms_per_step": 1000.0 / value,
+        "steps": n_steps, "steps_requested": args.steps, "pairs_per_step": done // max(n_steps, 1),
+        "warmup": min(args.warmup, 2), "ms_per_step": 1000.0 * secs / max(n_steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": f"{cpu.pairs_per_forward} pair(s) of the N=2048 workload per step (one forward), "
                                                      "fp32, torch CPU"},
