@@ -96,3 +96,30 @@ def test_superpoint_header_symbols_are_exported_and_host_mirror_contract():
     with pytest.raises(RuntimeError):
         m({"image": torch.zeros(1, 1, 64, 64)})  # CPU tensor: no CPU path
     m.load_state_dict(sps.make_superpoint_state_dict(0))
+
+
+@pytest.mark.parametrize("h,w,conf", [
+    (8, 8, dict(remove_borders=0)),                       # one detector cell
+    (9, 15, dict(remove_borders=1, nms_radius=1)),        # neither extent a multiple of 8, one cell row
+    (17, 33, dict(remove_borders=2)),
+    (67, 45, {}),                                         # portrait, odd at every pooling level
+    (24, 131, dict(max_num_keypoints=20)),
+])
+def test_cuda_functors_on_host_any_image_size_vs_oracle(emul, h, w, conf):
+    """Image extents that are not multiples of 8 (floor poolings, superpoint.py:173-179; score map over the 8-aligned
+    top-left area, 188-190): the CUDA functors against the Python oracle, which is pinned to the reference on the
+    fixtures (among them the odd-sized sp_odd_203x317)."""
+    from oracle import superpoint_oracle as spo
+
+    torch.set_grad_enabled(False)
+    wts = sps.make_superpoint_state_dict(0)
+    image = sps.make_image(h, w, 1, 100 + h)
+    full = dict(nms_radius=4, max_num_keypoints=None, detection_threshold=0.0005, remove_borders=4)
+    full.update(conf)
+    ref = spo.forward(wts, image, **full)
+    kp, sc, de, cnt = run_emulated(emul, wts, image, full)
+    n = int(cnt[0])
+    assert n == ref["keypoints"][0].shape[0] and n > 0
+    assert torch.equal(kp[0, :n], ref["keypoints"][0])
+    assert float((sc[0, :n] - ref["keypoint_scores"][0]).abs().max()) <= 2e-5
+    assert float((de[0, :n] - ref["descriptors"][0]).abs().max()) <= 2e-6
