@@ -97,7 +97,8 @@ extern "C" int sp_forward(SpHandle* h, const float* image, int32_t B, int32_t H,
   int rc;
   // Thumbnails (fewer than 64 x 64 pixels) take the CUDA-core path in either precision mode: the 128-row tensor-core tiles
   // would be mostly padding, and at 9 x 15 / 17 x 33 the tensor-core scores were measured up to 8e-4 off the oracle (same
-  // keypoint sets; 8 x 8, 24 x 131, 67 x 45 and every fixture within 1.5e-4) -- not investigated, so not used there.
+  // keypoint sets; 8 x 8, 24 x 131, 67 x 45 and every fixture within 1.5e-4; split-bf16 rounding alone predicts <= 6e-6)
+  // -- an open defect at those shapes, so the path is not used for thumbnails.
   const bool use_tc = h->tc && (long)H * W >= 64L * 64L;
   if (use_tc) {  // convolutions on the tensor cores, then the shared post-processing functors
     rc = sp_tc_backbone(h->tc, h->wts, image, B, H, W, (char*)workspace + w.bytes, w.logits, w.dense, stream);
